@@ -1,0 +1,309 @@
+// common.cuh -- shared device structs and helpers for the ATSC sm_100a kernels.
+//
+// Reference citations are relative to /root/reference/atsc/src/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace atsc {
+
+// Bitdepth variant index (optimizer/utils.rs:20-26)
+enum { BD_F64 = 0, BD_I32 = 1, BD_I16 = 2, BD_U8 = 3 };
+// Compressor variant index (compressor/mod.rs:34-44)
+enum { C_NOOP = 0, C_FFT = 1, C_IDW = 2, C_CONSTANT = 3, C_POLY = 4, C_AUTO = 5, C_RLE = 6 };
+
+constexpr int MAX_FRAME = 131072;      // optimizer/mod.rs:27 MAX_FRAME_SIZE
+constexpr int MAX_FFT_LEN = 139968;    // next_size(131072) = 2^6 * 3^7
+constexpr int BLOCK = 1024;            // threads per CTA for the per-frame kernels
+
+constexpr uint8_t TIE_FFT_LOOP = 1, TIE_POLY_LOOP = 2, TIE_SELECT = 4, TIE_FFT_TOPK = 8;
+
+// One record per frame, lives in device memory for the duration of a wave.
+struct FrameWork {
+    // ---- input
+    uint64_t off;  // first sample in the device sample buffer
+    uint32_t len;  // N
+    uint8_t comp;  // requested compressor
+    uint8_t bounded;
+    uint8_t select_only;  // sampled-selection pass (frame/mod.rs:94-105): only the winner is wanted
+    uint8_t forced;  // Auto frames only: 0xFF = pick freely, else the compressor the sampled pass chose
+    // ---- stats (optimizer/utils.rs DataStats)
+    double vmin, vmax;
+    uint8_t bitdepth, fractional, is_const, f32_const;
+    uint32_t n_runs;
+    uint32_t rle_idx_bytes;
+    // ---- which candidates run
+    uint8_t need_poly, need_rle, need_fft, poly_type;  // poly_type: 0 Catmull-Rom, 1 IDW
+    // ---- polynomial / idw candidate
+    uint32_t poly_step, poly_npts, poly_size;
+    uint16_t poly_iters;
+    uint8_t poly_tie, poly_valid;
+    double poly_err;
+    // ---- rle candidate
+    uint32_t rle_groups, rle_size;
+    uint8_t rle_valid, pad1[3];
+    // ---- fft candidate
+    uint32_t fft_count, fft_size;
+    uint16_t fft_iters;
+    uint8_t fft_tie, fft_valid;  // fft_valid: 1 evaluated to the reference's stopping point, 2 pruned (cannot win)
+    double fft_err;
+    uint64_t fft_list_off;  // entry offset into the wave's FftEntry arena
+    uint32_t fft_list_cap;
+    int32_t geom;        // index into the FftGeom table, -1 = direct DFT (N < 128)
+    uint32_t aux_size;   // Noop / Constant payload size
+    uint32_t pad2;
+    // ---- result
+    uint8_t winner, near_tie;
+    uint16_t iterations;
+    uint32_t payload_len;
+    uint64_t payload_off;
+    double error;
+};
+
+// sorted (descending |z|) spectrum entry kept for emission
+struct FftEntry {
+    uint32_t bin;  // true bin index 0..L/2 (u16 wrap applied at use, fft.rs:242)
+    float re, im;
+};
+
+// ----------------------------------------------------------------------------
+// bincode varint helpers (compressor/mod.rs:126-130, bincode 2 "standard")
+// ----------------------------------------------------------------------------
+__host__ __device__ inline uint32_t varint_len(uint64_t u) {
+    return u < 251 ? 1u : u < 65536ull ? 3u : u < 4294967296ull ? 5u : 9u;
+}
+__host__ __device__ inline uint64_t zigzag64(int64_t n) {
+    return ((uint64_t)n << 1) ^ (uint64_t)(n >> 63);
+}
+__host__ __device__ inline int64_t unzigzag64(uint64_t u) {
+    return (int64_t)(u >> 1) ^ -(int64_t)(u & 1);
+}
+__host__ __device__ inline uint32_t put_varint(uint8_t *p, uint64_t u) {
+    if (u < 251) {
+        p[0] = (uint8_t)u;
+        return 1;
+    }
+    if (u < 65536ull) {
+        p[0] = 251;
+        p[1] = (uint8_t)u;
+        p[2] = (uint8_t)(u >> 8);
+        return 3;
+    }
+    if (u < 4294967296ull) {
+        p[0] = 252;
+        for (int i = 0; i < 4; i++) p[1 + i] = (uint8_t)(u >> (8 * i));
+        return 5;
+    }
+    p[0] = 253;
+    for (int i = 0; i < 8; i++) p[1 + i] = (uint8_t)(u >> (8 * i));
+    return 9;
+}
+// length of the varint that starts with byte b (0 = invalid marker)
+__host__ __device__ inline uint32_t varint_len_from_first(uint8_t b) {
+    return b < 251 ? 1u : b == 251 ? 3u : b == 252 ? 5u : b == 253 ? 9u : 17u;
+}
+__host__ __device__ inline uint64_t get_varint(const uint8_t *p, uint32_t *len) {
+    uint8_t b = p[0];
+    if (b < 251) {
+        *len = 1;
+        return b;
+    }
+    int nb = b == 251 ? 2 : b == 252 ? 4 : 8;
+    uint64_t v = 0;
+    for (int i = 0; i < nb; i++) v |= (uint64_t)p[1 + i] << (8 * i);
+    *len = 1 + nb;
+    return v;
+}
+__host__ __device__ inline void put_bytes(uint8_t *p, const void *src, int n) {
+    const uint8_t *s = (const uint8_t *)src;
+    for (int i = 0; i < n; i++) p[i] = s[i];
+}
+
+// ----------------------------------------------------------------------------
+// Rust `as` casts: saturating, NaN -> 0
+// ----------------------------------------------------------------------------
+__device__ inline int64_t rust_as_i64(double x) {
+    return __double2ll_rz(x);  // cvt.rzi.s64.f64 saturates, NaN -> 0x8000.. on some archs
+}
+__device__ inline int32_t rust_as_i32(double x) {
+    if (x != x) return 0;
+    if (x >= 2147483647.0) return 2147483647;
+    if (x <= -2147483648.0) return (int32_t)0x80000000;
+    return (int32_t)x;
+}
+__device__ inline int32_t rust_as_i16(double x) {
+    if (x != x) return 0;
+    if (x >= 32767.0) return 32767;
+    if (x <= -32768.0) return -32768;
+    return (int32_t)x;
+}
+__device__ inline uint32_t rust_as_u8(double x) {
+    if (x != x) return 0;
+    if (x >= 255.0) return 255;
+    if (x <= 0.0) return 0;
+    return (uint32_t)x;
+}
+__device__ inline int64_t rust_as_i64_safe(double x) {
+    if (x != x) return 0;
+    if (x >= 9223372036854775808.0) return 0x7FFFFFFFFFFFFFFFll;
+    if (x <= -9223372036854775808.0) return (int64_t)0x8000000000000000ull;
+    return (int64_t)x;
+}
+
+// number of payload bytes one stored value takes at a given bitdepth
+// (polynomial.rs:61-81, rle.rs:47-64, constant.rs:44-61)
+__device__ inline uint32_t value_bytes(double v, int bitdepth) {
+    switch (bitdepth) {
+        case BD_U8: return 1;
+        case BD_I16: return varint_len(zigzag64((int64_t)rust_as_i16(v)));
+        case BD_I32: return varint_len(zigzag64((int64_t)rust_as_i32(v)));
+        default: return 8;
+    }
+}
+__device__ inline uint32_t put_value(uint8_t *p, double v, int bitdepth) {
+    switch (bitdepth) {
+        case BD_U8: p[0] = (uint8_t)rust_as_u8(v); return 1;
+        case BD_I16: return put_varint(p, zigzag64((int64_t)rust_as_i16(v)));
+        case BD_I32: return put_varint(p, zigzag64((int64_t)rust_as_i32(v)));
+        default: put_bytes(p, &v, 8); return 8;
+    }
+}
+
+// ----------------------------------------------------------------------------
+// utils/mod.rs:61-74 rounding.  No FMA contraction: explicit _rn intrinsics.
+// ----------------------------------------------------------------------------
+// round half away from zero (Rust f64::round == C round)
+__device__ inline double round5_exact(double x) {
+    // (x * 1e5).round() / 1e5 with a true IEEE division
+    return __ddiv_rn(round(__dmul_rn(x, 100000.0)), 100000.0);
+}
+__device__ inline double round_and_limit5(double x, double mn, double mx) {
+    double out = round5_exact(x);
+    if (out < mn) return mn;
+    if (out > mx) return mx;
+    return out;
+}
+__device__ inline double round_f64_dec(double x, int decimals) {
+    double y = decimals == 3 ? 1000.0 : decimals == 4 ? 10000.0 : 100000.0;
+    return __ddiv_rn(round(__dmul_rn(x, y)), y);
+}
+
+// optimizer/utils.rs:115-160 split_n: (integer part as i64, fraction != 0)
+__device__ inline int64_t split_n(double x, bool *frac_nz) {
+    uint64_t bits = (uint64_t)__double_as_longlong(x);
+    bool neg = ((int64_t)bits) < 0;
+    int exponent = (int)((bits >> 52) & 0x7FF);
+    uint64_t m = (bits & ((1ull << 52) - 1)) | (1ull << 52);
+    int64_t mant = neg ? -(int64_t)m : (int64_t)m;
+    int shl = exponent + (64 - 53 - 1023 + 1);
+    if (shl <= 0) {
+        int shr = -shl;
+        if (shr < 64) {
+            *frac_nz = (((uint64_t)mant) >> shr) != 0;
+            return 0;
+        }
+        *frac_nz = false;
+        return 0;
+    } else if (shl < 64) {
+        *frac_nz = (((uint64_t)mant) << shl) != 0;
+        return mant >> (64 - shl);
+    } else if (shl < 128) {
+        *frac_nz = false;
+        return (int64_t)(((uint64_t)mant) << (shl - 64));
+    }
+    *frac_nz = false;
+    return 0;
+}
+// optimizer/utils.rs:91-113
+__device__ inline int bitdepth_of(int64_t max_int, int64_t min_int) {
+    int bd = max_int <= 255 ? 8 : max_int <= 32767 ? 16 : max_int <= 2147483647ll ? 32 : 64;
+    int bs = (min_int >= 0 && min_int <= 255) ? 8
+             : min_int >= -32768             ? 16
+             : min_int >= -2147483648ll      ? 32
+                                             : 64;
+    int b = bd > bs ? bd : bs;
+    return b == 8 ? BD_U8 : b == 16 ? BD_I16 : b == 32 ? BD_I32 : BD_F64;
+}
+
+// ----------------------------------------------------------------------------
+// block-wide primitives (BLOCK threads, warp shuffles + one smem hop)
+// ----------------------------------------------------------------------------
+__device__ inline double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+// deterministic tree sum; result valid in every thread. scratch: >= 33 doubles
+__device__ inline double block_sum(double v, double *scratch) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = lane < (blockDim.x >> 5) ? scratch[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+__device__ inline uint32_t warp_sum_u32(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+// scratch: >= 33 uint32
+__device__ inline uint32_t block_sum_u32(uint32_t v, uint32_t *scratch) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum_u32(v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t t = lane < (blockDim.x >> 5) ? scratch[lane] : 0u;
+        t = warp_sum_u32(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+// exclusive scan of one uint32 per thread; returns exclusive prefix, *total = block sum.
+// scratch: >= 33 uint32
+__device__ inline uint32_t block_excl_scan_u32(uint32_t v, uint32_t *scratch, uint32_t *total) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) scratch[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t t = lane < (blockDim.x >> 5) ? scratch[lane] : 0u;
+        uint32_t ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += u;
+        }
+        scratch[lane] = ti - t;  // exclusive warp offsets
+        if (lane == 31) scratch[32] = ti;
+    }
+    __syncthreads();
+    uint32_t res = scratch[w] + inc - v;
+    *total = scratch[32];
+    return res;
+}
+
+// dynamic work queue: every CTA pulls the next item index
+__device__ inline int queue_next(unsigned int *counter, int *smem_slot) {
+    __syncthreads();
+    if (threadIdx.x == 0) *smem_slot = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    return *smem_slot;
+}
+
+}  // namespace atsc

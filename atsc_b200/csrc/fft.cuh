@@ -1,0 +1,500 @@
+// fft.cuh -- batched f32 FFT engine + FFT compressor loop, device side.
+//   FFT::compress_bounded  fft.rs:288-362     FFT::fft_trim        fft.rs:231-257
+//   FFT::gibbs_sizing      fft.rs:184-204     get_mirrored_freqs   fft.rs:401-422
+//   FFT::round             fft.rs:208-218     FFT::to_data         fft.rs:426-462
+//
+// Engine (prototype with the same index math: tools/fft_prototype.py):
+//  * length L = 2^a 3^b.  Even L uses the real-input trick: complex length M = L/2.
+//  * four-step M = M1 x M2 with both sub-lengths done in shared memory by a Stockham
+//    DIF autosort, 32 transforms side by side (batch index = lane, so twiddles are warp
+//    uniform and every shared access is unit stride).
+//  * the spectrum stays in "permuted" order S[k1][k2] = Z[k1 + M1*k2]; the inverse consumes
+//    that order directly, so there is no transpose pass.
+//  * the inverse's first pass builds its input tile straight from the sparse top-k list.
+#pragma once
+#include "common.cuh"
+
+namespace atsc {
+
+constexpr int FFT_TLEN = 320;                                   // max sub-FFT length
+constexpr int FFT_FP = 33;                                      // padded batch stride (float2 units)
+constexpr int FFT_TILE_F2 = FFT_TLEN * FFT_FP;                  // float2 per tile buffer
+constexpr int FFT_SMEM_BYTES = 2 * FFT_TILE_F2 * (int)sizeof(float2);  // 168,960 B
+constexpr int FFT_KCAP = 16384;                                 // max list entries when compressing (pow2 for the sort)
+constexpr int FFT_DEC_KCAP = 65536;                             // max entries accepted when decoding (pos is a u16)
+constexpr int FFT_SCHED = 23;                                   // fft.rs:348-352
+
+struct FftGeom {
+    uint32_t L, real, M, M1, M2, Bn;
+    uint32_t ns1, ns2;
+    uint8_t rad1[12], rad2[12];
+    const float2 *twM;  // exp(-2 pi i j / M), j < M
+    const float2 *tw1;  // exp(-2 pi i j / M1)
+    const float2 *tw2;  // exp(-2 pi i j / M2)
+    const float2 *twL;  // exp(-2 pi i j / L), j <= M
+    const float2 *twA;  // [M1][32]: exp(-2 pi i e f / M)
+    const float2 *twB;  // [M2][32]
+};
+
+// per-CTA-slot global workspace
+struct FftWs {
+    float2 *W;       // [Mmax]   four-step intermediate / permuted spectrum
+    float2 *Xd;      // [Bnmax]  half spectrum, natural order
+    uint32_t *keys;  // [Bnmax]  f32 bits of |X[k]|
+    uint32_t *rank;  // [Bnmax]  list rank per bin (+1), 0 = not in list
+    uint32_t *locD, *locM, *ovr;  // [FFT_DEC_KCAP]
+    float2 *cD, *cM;              // [FFT_DEC_KCAP]
+    FftEntry *dlist;              // [FFT_DEC_KCAP] decode-side entry list
+};
+
+__device__ inline float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ inline float2 cmulc(float2 a, float2 b) {  // a * conj(b)
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ inline float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ inline float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// ---------------------------------------------------------------------------------------
+// 32-wide batched Stockham DIF FFT of length `len` in shared memory.
+// Element e of transform f lives at x[e*FFT_FP + f].  Returns the buffer with the result.
+// ---------------------------------------------------------------------------------------
+template <bool INV>
+__device__ inline float2 *tile_fft(float2 *x, float2 *y, int len, const uint8_t *rad, int ns,
+                                   const float2 *__restrict__ tw, int nb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    int n = len, s = 1;
+    for (int st = 0; st < ns; st++) {
+        const int r = rad[st];
+        const int m = n / r;
+        const int nbf = len / r;
+        const int tws = len / n;
+        if (lane < nb) {
+            for (int b = warp; b < nbf; b += nw) {
+                const int p = b / s, q = b - p * s;
+                const float2 *xi = x + (q + s * p) * FFT_FP + lane;
+                float2 *yo = y + (q + s * r * p) * FFT_FP + lane;
+                const int xs = s * m * FFT_FP;  // input stride between radix legs
+                const int ys = s * FFT_FP;      // output stride between radix legs
+                if (r == 4) {
+                    float2 a0 = xi[0], a1 = xi[xs], a2 = xi[2 * xs], a3 = xi[3 * xs];
+                    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
+                    // forward: -i*t3 ; inverse: +i*t3
+                    float2 jt3 = INV ? make_float2(-t3.y, t3.x) : make_float2(t3.y, -t3.x);
+                    float2 b0 = cadd(t0, t2), b1 = cadd(t1, jt3), b2 = csub(t0, t2), b3 = csub(t1, jt3);
+                    float2 w1 = tw[p * tws], w2 = tw[2 * p * tws], w3 = tw[3 * p * tws];
+                    yo[0] = b0;
+                    yo[ys] = INV ? cmulc(b1, w1) : cmul(b1, w1);
+                    yo[2 * ys] = INV ? cmulc(b2, w2) : cmul(b2, w2);
+                    yo[3 * ys] = INV ? cmulc(b3, w3) : cmul(b3, w3);
+                } else if (r == 3) {
+                    float2 a0 = xi[0], a1 = xi[xs], a2 = xi[2 * xs];
+                    float2 t = cadd(a1, a2), d = csub(a1, a2);
+                    float2 mm = make_float2(a0.x - 0.5f * t.x, a0.y - 0.5f * t.y);
+                    const float c = 0.86602540378443864676f;
+                    float2 rot = INV ? make_float2(-c * d.y, c * d.x) : make_float2(c * d.y, -c * d.x);
+                    float2 b0 = cadd(a0, t), b1 = cadd(mm, rot), b2 = csub(mm, rot);
+                    float2 w1 = tw[p * tws], w2 = tw[2 * p * tws];
+                    yo[0] = b0;
+                    yo[ys] = INV ? cmulc(b1, w1) : cmul(b1, w1);
+                    yo[2 * ys] = INV ? cmulc(b2, w2) : cmul(b2, w2);
+                } else {  // r == 2
+                    float2 a0 = xi[0], a1 = xi[xs];
+                    float2 w1 = tw[p * tws];
+                    float2 b1 = csub(a0, a1);
+                    yo[0] = cadd(a0, a1);
+                    yo[ys] = INV ? cmulc(b1, w1) : cmul(b1, w1);
+                }
+            }
+        }
+        __syncthreads();
+        float2 *t = x;
+        x = y;
+        y = t;
+        n = m;
+        s *= r;
+    }
+    return x;
+}
+
+// multiply tile element (e, f) by W_M^{+-(e * (base + f))} = twM[e*base] * twEF[e][f]
+template <bool INV>
+__device__ inline void tile_twiddle(float2 *x, int len, int nb, uint32_t base,
+                                    const float2 *__restrict__ twM,
+                                    const float2 *__restrict__ twEF) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane < nb) {
+        for (int e = warp; e < len; e += nw) {
+            float2 w = cmul(twM[(uint32_t)e * base], twEF[e * 32 + lane]);
+            float2 v = x[e * FFT_FP + lane];
+            x[e * FFT_FP + lane] = INV ? cmulc(v, w) : cmul(v, w);
+        }
+    }
+    __syncthreads();
+}
+
+// rows r0..r0+nb-1 of the [M1][M2] global matrix <-> tile (element = column index)
+__device__ inline void tile_load_rows(float2 *x, const float2 *__restrict__ W, int M2, int r0, int nb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < nb) {
+        const float2 *row = W + (size_t)(r0 + warp) * M2;
+        for (int e = lane; e < M2; e += 32) x[e * FFT_FP + warp] = row[e];
+    }
+    __syncthreads();
+}
+__device__ inline void tile_store_rows(const float2 *x, float2 *__restrict__ W, int M2, int r0, int nb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < nb) {
+        float2 *row = W + (size_t)(r0 + warp) * M2;
+        for (int e = lane; e < M2; e += 32) row[e] = x[e * FFT_FP + warp];
+    }
+    __syncthreads();
+}
+// columns c0..c0+nb-1 (element = row index)
+__device__ inline void tile_load_cols(float2 *x, const float2 *__restrict__ W, int M1, int M2, int c0, int nb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane < nb)
+        for (int e = warp; e < M1; e += nw) x[e * FFT_FP + lane] = W[(size_t)e * M2 + c0 + lane];
+    __syncthreads();
+}
+__device__ inline void tile_store_cols(const float2 *x, float2 *__restrict__ W, int M1, int M2, int c0, int nb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane < nb)
+        for (int e = warp; e < M1; e += nw) W[(size_t)e * M2 + c0 + lane] = x[e * FFT_FP + lane];
+    __syncthreads();
+}
+
+// padded ("gibbs sized", fft.rs:184-204) sample j of the frame, as the f32 the reference feeds
+// to the FFT (fft.rs:221-228)
+__device__ inline double padded_sample(const double *__restrict__ d, uint32_t N, uint32_t prefix, uint32_t j) {
+    uint32_t i = j < prefix ? 0u : j - prefix;
+    if (i >= N) i = N - 1;
+    return d[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// forward transform of the padded frame -> Xd[k], keys[k], k < Bn
+// ---------------------------------------------------------------------------------------
+__device__ inline void fft_forward(const double *__restrict__ d, uint32_t N, uint32_t prefix,
+                                   const FftGeom &g, FftWs ws, float2 *sm) {
+    float2 *bufA = sm, *bufB = sm + FFT_TILE_F2;
+    const int M1 = g.M1, M2 = g.M2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    // pass 1: column tiles; input built from the samples
+    for (int c0 = 0; c0 < M2; c0 += 32) {
+        int nb = min(32, M2 - c0);
+        if (lane < nb) {
+            for (int e = warp; e < M1; e += nw) {
+                uint32_t n = (uint32_t)e * M2 + c0 + lane;
+                float2 z;
+                if (g.real) {
+                    z.x = (float)padded_sample(d, N, prefix, 2 * n);
+                    z.y = (float)padded_sample(d, N, prefix, 2 * n + 1);
+                } else {
+                    z.x = (float)padded_sample(d, N, prefix, n);
+                    z.y = 0.f;
+                }
+                bufA[e * FFT_FP + lane] = z;
+            }
+        }
+        __syncthreads();
+        float2 *res = tile_fft<false>(bufA, bufB, M1, g.rad1, g.ns1, g.tw1, nb);
+        tile_twiddle<false>(res, M1, nb, (uint32_t)c0, g.twM, g.twA);
+        tile_store_cols(res, ws.W, M1, M2, c0, nb);
+    }
+    // pass 2: row tiles, in place
+    for (int r0 = 0; r0 < M1; r0 += 32) {
+        int nb = min(32, M1 - r0);
+        tile_load_rows(bufA, ws.W, M2, r0, nb);
+        float2 *res = tile_fft<false>(bufA, bufB, M2, g.rad2, g.ns2, g.tw2, nb);
+        tile_store_rows(res, ws.W, M2, r0, nb);
+    }
+    __threadfence_block();
+    __syncthreads();
+    // post-process: X[k] for k = 0..L/2 in natural order + |X[k]| keys
+    const uint32_t M = g.M;
+    for (uint32_t k = threadIdx.x; k < g.Bn; k += blockDim.x) {
+        float2 X;
+        if (g.real) {
+            uint32_t ka = k % M, kb = (M - k) % M;
+            float2 Zk = ws.W[(size_t)(ka % M1) * M2 + ka / M1];
+            float2 Zm = ws.W[(size_t)(kb % M1) * M2 + kb / M1];
+            Zm.y = -Zm.y;  // conj
+            float2 sum = cadd(Zk, Zm), dif = csub(Zk, Zm);
+            float2 t = cmul(g.twL[k], dif);  // twL * (Zk - conj Zmk)
+            // X = 0.5 * (sum - i * t)
+            X.x = 0.5f * (sum.x + t.y);
+            X.y = 0.5f * (sum.y - t.x);
+        } else {
+            X = ws.W[(size_t)(k % M1) * M2 + k / M1];
+        }
+        ws.Xd[k] = X;
+        // Complex<f32>::norm() == hypotf; via f64 sqrt to stay correctly rounded
+        double nr = sqrt((double)X.x * (double)X.x + (double)X.y * (double)X.y);
+        ws.keys[k] = __float_as_uint((float)nr);
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// top-K of the half spectrum by |z| (fft.rs:231-257), descending, ties by lower bin.
+// Writes list[0..K) and returns K = min(kmax, #nonzero bins).
+// ---------------------------------------------------------------------------------------
+__device__ inline uint32_t fft_topk(uint32_t Bn, FftWs ws, uint32_t kmax, FftEntry *list,
+                                    unsigned long long *sm64, uint32_t *sh, bool *tie_at_cut) {
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    uint32_t *hist = (uint32_t *)sm64;  // 256 bins (phase-local reuse of the big smem region)
+    // number of non-zero bins
+    uint32_t loc = 0;
+    for (uint32_t b = t; b < Bn; b += T) loc += ws.keys[b] != 0u;
+    uint32_t nnz = block_sum_u32(loc, sh);
+    uint32_t K = min(min(kmax, nnz), (uint32_t)FFT_KCAP);
+    *tie_at_cut = false;
+    if (K == 0) return 0;
+    // radix select the K-th largest key
+    uint32_t prefix = 0, remaining = K;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (uint32_t i = t; i < 256; i += T) hist[i] = 0;
+        __syncthreads();
+        for (uint32_t b = t; b < Bn; b += T) {
+            uint32_t key = ws.keys[b];
+            bool in = shift == 24 ? true : (key >> (shift + 8)) == prefix;
+            if (in) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (t == 0) {
+            uint32_t acc = 0;
+            int dsel = 0;
+            for (int dgt = 255; dgt >= 0; dgt--) {
+                if (acc + hist[dgt] >= remaining) {
+                    dsel = dgt;
+                    break;
+                }
+                acc += hist[dgt];
+            }
+            sh[102] = (uint32_t)dsel;
+            sh[103] = acc;
+        }
+        __syncthreads();
+        prefix = (prefix << 8) | sh[102];
+        remaining -= sh[103];
+        __syncthreads();
+    }
+    const uint32_t Tkey = prefix;       // K-th largest key
+    const uint32_t take_eq = remaining;  // how many bins with key == Tkey are taken (lowest bins first)
+    // ordered compaction into composite sort keys
+    uint32_t P = 1;
+    while (P < K) P <<= 1;
+    unsigned long long *S = sm64;
+    __syncthreads();
+    uint32_t base = 0, eqbase = 0, eq_total = 0;
+    for (uint32_t b0 = 0; b0 < Bn; b0 += T) {
+        uint32_t b = b0 + t;
+        uint32_t key = b < Bn ? ws.keys[b] : 0u;
+        bool gt = b < Bn && key > Tkey;
+        bool eq = b < Bn && key == Tkey;
+        uint32_t eqtot;
+        uint32_t eqrank = eqbase + block_excl_scan_u32(eq ? 1u : 0u, sh, &eqtot);
+        __syncthreads();
+        bool sel = gt || (eq && eqrank < take_eq);
+        uint32_t tot;
+        uint32_t pos = base + block_excl_scan_u32(sel ? 1u : 0u, sh, &tot);
+        if (sel) S[pos] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - b);
+        base += tot;
+        eqbase += eqtot;
+        eq_total += eqtot;
+        __syncthreads();
+    }
+    for (uint32_t i = K + t; i < P; i += T) S[i] = 0ull;
+    __syncthreads();
+    // bitonic sort, descending
+    for (uint32_t k2 = 2; k2 <= P; k2 <<= 1) {
+        for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = t; i < P; i += T) {
+                uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = S[i], b = S[ixj];
+                    bool desc = (i & k2) == 0;
+                    if (desc ? (a < b) : (a > b)) {
+                        S[i] = b;
+                        S[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t r = t; r < K; r += T) {
+        uint32_t bin = 0xFFFFFFFFu - (uint32_t)(S[r] & 0xFFFFFFFFull);
+        float2 X = ws.Xd[bin];
+        FftEntry e;
+        e.bin = bin;
+        e.re = X.x;
+        e.im = X.y;
+        list[r] = e;
+    }
+    *tie_at_cut = eq_total > take_eq;
+    __syncthreads();
+    return K;
+}
+
+// after fft_topk: S (sm64) still holds the sorted composite keys; true if a cut after the
+// first c entries separates two bins with equal |z|
+__device__ inline bool fft_cut_splits_tie(const unsigned long long *S, uint32_t c, uint32_t K) {
+    return c > 0 && c < K && (uint32_t)(S[c - 1] >> 32) == (uint32_t)(S[c] >> 32);
+}
+
+// ---------------------------------------------------------------------------------------
+// per-entry scatter coefficients for the inverse (see tools/fft_prototype.py)
+// ---------------------------------------------------------------------------------------
+// set_ovr=false: ws.ovr was filled by the caller (decode path: "last entry per position wins")
+__device__ inline void fft_prepare_entries(const FftGeom &g, FftWs ws, const FftEntry *list,
+                                           uint32_t K, bool alias, bool set_ovr = true) {
+    const uint32_t M = g.M, M1 = g.M1, L = g.L;
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    if (alias) {
+        for (uint32_t b = t; b < g.Bn; b += T) ws.rank[b] = 0;
+        __syncthreads();
+        for (uint32_t r = t; r < K; r += T) ws.rank[list[r].bin] = r + 1;
+        __syncthreads();
+    }
+    for (uint32_t r = t; r < K; r += T) {
+        FftEntry e = list[r];
+        uint32_t p = alias ? (e.bin & 0xFFFFu) : e.bin;  // `pos as u16` (fft.rs:242)
+        uint32_t ov = 0xFFFFFFFFu;
+        if (alias) {
+            uint32_t partner = e.bin ^ 0x10000u;
+            if (partner < g.Bn) {
+                uint32_t pr = ws.rank[partner];
+                if (pr) ov = pr - 1;
+            }
+        }
+        if (set_ovr) ws.ovr[r] = ov;
+        float2 z = make_float2(e.re, e.im);
+        uint32_t lD = 0xFFFFFFFFu, lM = 0xFFFFFFFFu;
+        float2 cD = make_float2(0.f, 0.f), cM = make_float2(0.f, 0.f);
+        if (g.real) {
+            if (p == 0) {
+                lD = 0;
+                cD = make_float2(z.x, z.x);  // re * (1 + i)
+            } else if (p == M) {
+                lM = 0;
+                cM = make_float2(z.x, -z.x);  // re * (1 - i) at k = 0
+            } else if (p < M) {
+                float2 w = g.twL[p];  // (cos, -sin)
+                float c = w.x, s = -w.y;
+                cD = cmul(z, make_float2(1.f - s, c));
+                lD = ((p % M1) << 16) | (p / M1);
+                uint32_t k = M - p;
+                cM = cmul(make_float2(z.x, -z.y), make_float2(1.f + s, c));
+                lM = ((k % M1) << 16) | (k / M1);
+            }
+        } else {
+            if (p == 0) {
+                lD = 0;
+                cD = make_float2(z.x, 0.f);
+            } else if (p < L) {
+                lD = ((p % M1) << 16) | (p / M1);
+                cD = z;
+                uint32_t k = L - p;
+                lM = ((k % M1) << 16) | (k / M1);
+                cM = make_float2(z.x, -z.y);
+            }
+        }
+        ws.locD[r] = lD;
+        ws.locM[r] = lM;
+        ws.cD[r] = cD;
+        ws.cM[r] = cM;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// inverse transform of the first `c` list entries; Epi(j, value) is called once for every
+// time index j < L with the unnormalised real output (all threads participate).
+// ---------------------------------------------------------------------------------------
+template <class Epi>
+__device__ inline void fft_inverse(const FftGeom &g, FftWs ws, uint32_t c, float2 *sm, Epi epi) {
+    float2 *bufA = sm, *bufB = sm + FFT_TILE_F2;
+    const int M1 = g.M1, M2 = g.M2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    // pass 1: row tiles built from the sparse list
+    for (int r0 = 0; r0 < M1; r0 += 32) {
+        int nb = min(32, M1 - r0);
+        for (uint32_t i = t; i < (uint32_t)M2 * FFT_FP; i += T) bufA[i] = make_float2(0.f, 0.f);
+        __syncthreads();
+        for (uint32_t r = t; r < c; r += T) {
+            uint32_t ov = ws.ovr[r];
+            if (ov > r && ov < c) continue;  // overwritten by a later aliased entry (fft.rs:411-420)
+            uint32_t l = ws.locD[r];
+            if (l != 0xFFFFFFFFu) {
+                uint32_t f = (l >> 16) - (uint32_t)r0;
+                if (f < 32u) bufA[(l & 0xFFFFu) * FFT_FP + f] = ws.cD[r];
+            }
+        }
+        __syncthreads();
+        for (uint32_t r = t; r < c; r += T) {
+            uint32_t ov = ws.ovr[r];
+            if (ov > r && ov < c) continue;
+            uint32_t l = ws.locM[r];
+            if (l != 0xFFFFFFFFu) {
+                uint32_t f = (l >> 16) - (uint32_t)r0;
+                if (f < 32u) {
+                    float2 *q = &bufA[(l & 0xFFFFu) * FFT_FP + f];
+                    *q = cadd(*q, ws.cM[r]);
+                }
+            }
+        }
+        __syncthreads();
+        float2 *res = tile_fft<true>(bufA, bufB, M2, g.rad2, g.ns2, g.tw2, nb);
+        tile_twiddle<true>(res, M2, nb, (uint32_t)r0, g.twM, g.twB);
+        tile_store_rows(res, ws.W, M2, r0, nb);
+    }
+    __threadfence_block();
+    __syncthreads();
+    // pass 2: column tiles + epilogue
+    for (int c0 = 0; c0 < M2; c0 += 32) {
+        int nb = min(32, M2 - c0);
+        tile_load_cols(bufA, ws.W, M1, M2, c0, nb);
+        float2 *res = tile_fft<true>(bufA, bufB, M1, g.rad1, g.ns1, g.tw1, nb);
+        if (lane < nb) {
+            for (int e = warp; e < M1; e += nw) {
+                uint32_t n = (uint32_t)e * M2 + c0 + lane;
+                float2 v = res[e * FFT_FP + lane];
+                if (g.real) {
+                    epi(2 * n, v.x);
+                    epi(2 * n + 1, v.y);
+                } else {
+                    epi(n, v.x);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// FFT::round (fft.rs:208-218) of `re / len_f32`
+__device__ inline double fft_round(float x, float vminf, float vmaxf) {
+    double out = round5_exact((double)x);
+    if (out > (double)vmaxf) return (double)vmaxf;
+    if (out < (double)vminf) return (double)vminf;
+    return out;
+}
+
+// payload size of an FFT struct with the first c entries (fft.rs:119-130)
+__host__ __device__ inline uint32_t fft_payload_size(uint32_t c, uint32_t n_small_pos) {
+    return 1 + varint_len(c) + 11 * c - 2 * n_small_pos + 8;
+}
+
+// ---------------------------------------------------------------------------------------
+// direct O(n^2) path for frames shorter than 128 samples (no padding, fft.rs:305-309)
+// ---------------------------------------------------------------------------------------
+__device__ inline float2 unit_root(uint32_t num, uint32_t den, bool inverse) {
+    double s, c;
+    sincospi(2.0 * (double)(num % den) / (double)den, &s, &c);
+    return make_float2((float)c, (float)(inverse ? s : -s));
+}
+
+}  // namespace atsc

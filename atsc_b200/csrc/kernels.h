@@ -1,0 +1,62 @@
+// kernels.h -- host-callable launchers of the ATSC sm_100a kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "fft.cuh"
+#include "rle.cuh"
+
+namespace atsc {
+
+// base pointers of per-CTA-slot workspaces; slot s uses base + s * stride
+struct SlotPool {
+    // RLE sort (rle.cuh)
+    uint64_t *rle_k0, *rle_k1;
+    uint32_t *rle_i0, *rle_i1, *rle_bnd;
+    int rle_slots;
+    // FFT (fft.cuh)
+    float2 *fft_W, *fft_Xd, *fft_cD, *fft_cM;
+    uint32_t *fft_keys, *fft_rank, *fft_locD, *fft_locM, *fft_ovr;
+    FftEntry *fft_dlist;
+    int fft_slots;
+    // decode scratch
+    double *dec_pts;     // [MAX_FRAME + 8] per slot: decoded polynomial points / RLE values
+    uint32_t *dec_mark;  // [MAX_FRAME + 8] per slot: RLE run-start markers
+    uint32_t *dec_idx;   // [MAX_FRAME + 8] per slot
+    int dec_slots;
+};
+
+struct DecFrame {
+    uint64_t payload_off;
+    uint64_t out_off;
+    uint32_t payload_len;
+    uint32_t sample_count;
+    int32_t geom;
+    uint8_t comp;
+    uint8_t pad[3];
+};
+
+// compress pipeline; q = device array of >= 8 zeroed uint32 work-queue counters
+void launch_stats(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st);
+void launch_plan(FrameWork *fr, uint32_t n, cudaStream_t st);
+void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_err, const double *inv_d2,
+                 unsigned *q, cudaStream_t st);
+void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err, SlotPool pool,
+                unsigned *q, cudaStream_t st);
+void launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
+                SlotPool pool, FftEntry *arena, unsigned *q, cudaStream_t st);
+void launch_noop_size(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st);
+void launch_select(FrameWork *fr, uint32_t n, double max_err, cudaStream_t st);
+void launch_scan(FrameWork *fr, uint32_t n, unsigned long long *total, cudaStream_t st);
+void launch_emit(FrameWork *fr, uint32_t n, const double *samples, const FftGeom *geoms, SlotPool pool,
+                 const FftEntry *arena, uint8_t *payload, unsigned *q, cudaStream_t st);
+// decompress
+void launch_decode(const DecFrame *fr, uint32_t n, const uint8_t *payloads, double *out,
+                   const FftGeom *geoms, SlotPool pool, const double *inv_d2, uint32_t *status,
+                   unsigned *q, cudaStream_t st);
+void launch_inv_d2(double *inv_d2, uint32_t n, cudaStream_t st);
+
+int kernels_init();  // sets shared-memory attributes; returns cudaError_t as int
+
+}  // namespace atsc

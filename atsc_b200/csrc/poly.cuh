@@ -1,0 +1,253 @@
+// poly.cuh -- Polynomial (Catmull-Rom) and IDW compressors, device side.
+//   Polynomial::compress_bounded   polynomial.rs:209-277
+//   Polynomial::compress_hinted    polynomial.rs:279-305
+//   Polynomial::polynomial_to_data polynomial.rs:342-373  (splines 4.3.1 semantics)
+//   Polynomial::idw_to_data        polynomial.rs:375-393  (inverse_distance_weight 0.1.1)
+// All value arithmetic uses explicit _rn intrinsics: identical operation order to the
+// reference and no FMA contraction, so decompressed values are bit-exact.
+#pragma once
+#include "common.cuh"
+
+namespace atsc {
+
+// key layout of one candidate step (polynomial.rs:329-340 get_positions)
+struct PolyKeys {
+    uint32_t N, step, Kreg, K;  // Kreg = ceil(N/step) regular keys; K = Kreg (+1 if last index appended)
+};
+__host__ __device__ inline PolyKeys poly_keys(uint32_t N, uint32_t step) {
+    PolyKeys k;
+    k.N = N;
+    k.step = step;
+    k.Kreg = (N + step - 1) / step;
+    k.K = k.Kreg + (((k.Kreg - 1) * step != N - 1) ? 1u : 0u);
+    return k;
+}
+__device__ inline uint32_t poly_pos(const PolyKeys &k, uint32_t j) {
+    return j < k.Kreg ? j * k.step : k.N - 1;
+}
+
+// splines 4.3.1 cubic_hermite with (t, value) pairs x(before a), a, b, y(after b)
+__device__ inline double cubic_hermite(double t, double xt, double xv, double at, double av,
+                                       double bt, double bv, double yt, double yv) {
+    double two_t = __dmul_rn(t, 2.0);
+    double three_t = __dmul_rn(t, 3.0);
+    double t2 = __dmul_rn(t, t);
+    double t3 = __dmul_rn(t2, t);
+    double two_t3 = __dmul_rn(t2, two_t);
+    double two_t2 = __dmul_rn(t, two_t);
+    double three_t2 = __dmul_rn(t, three_t);
+    double seg = __dsub_rn(bt, at);
+    double m0 = __dmul_rn(__ddiv_rn(__dsub_rn(bv, xv), __dsub_rn(bt, xt)), seg);
+    double m1 = __dmul_rn(__ddiv_rn(__dsub_rn(yv, av), __dsub_rn(yt, at)), seg);
+    double c0 = __dmul_rn(av, __dadd_rn(__dsub_rn(two_t3, three_t2), 1.0));
+    double c1 = __dmul_rn(m0, __dadd_rn(__dsub_rn(t3, two_t2), t));
+    double c2 = __dmul_rn(bv, __dsub_rn(three_t2, two_t3));
+    double c3 = __dmul_rn(m1, __dsub_rn(t3, t2));
+    return __dadd_rn(__dadd_rn(__dadd_rn(c0, c1), c2), c3);
+}
+
+// Spline value at integer x.  `pts` yields the value of key j.
+template <class PtsFn>
+__device__ inline double poly_eval_at(const PolyKeys &k, uint32_t x, PtsFn pts) {
+    if (k.K == 1) return pts(0);
+    uint32_t lastpos = poly_pos(k, k.K - 1);
+    if (x >= lastpos) return pts(k.K - 1);  // clamped_sample: t >= last.t -> last.value
+    uint32_t i = x / k.step;                  // key i: pos[i] <= x < pos[i+1]
+    double at = (double)poly_pos(k, i), bt = (double)poly_pos(k, i + 1);
+    double nt = __ddiv_rn(__dsub_rn((double)x, at), __dsub_rn(bt, at));
+    bool catmull = (i > 0) && (k.K - i > 2);  // polynomial.rs:349
+    double av = pts(i), bv = pts(i + 1);
+    if (!catmull) {
+        // Linear: a * (1 - t) + b * t
+        return __dadd_rn(__dmul_rn(av, __dsub_rn(1.0, nt)), __dmul_rn(bv, nt));
+    }
+    return cubic_hermite(nt, (double)poly_pos(k, i - 1), pts(i - 1), at, av, bt, bv,
+                         (double)poly_pos(k, i + 2), pts(i + 2));
+}
+
+// IDW value at integer x: all K keys, power 2, sums in key order.
+// inv_d2[d] = 1 / (d*d) (IEEE), d >= 1.
+template <class PtsFn>
+__device__ inline double idw_eval_at(const PolyKeys &k, uint32_t x, PtsFn pts,
+                                     const double *__restrict__ inv_d2) {
+    // exact hit -> that key's value
+    if (x == k.N - 1) return pts(k.K - 1);
+    if (x % k.step == 0 && x / k.step < k.Kreg) return pts(x / k.step);
+    double S = 0.0;
+    for (uint32_t j = 0; j < k.K; j++) {
+        uint32_t p = poly_pos(k, j);
+        uint32_t d = p > x ? p - x : x - p;
+        S = __dadd_rn(S, inv_d2[d]);
+    }
+    double acc = 0.0;
+    for (uint32_t j = 0; j < k.K; j++) {
+        uint32_t p = poly_pos(k, j);
+        uint32_t d = p > x ? p - x : x - p;
+        acc = __dadd_rn(acc, __dmul_rn(__ddiv_rn(inv_d2[d], S), pts(j)));
+    }
+    return acc;
+}
+
+// MAPE (utils/error.rs:104-116) of one candidate step against the frame; block-wide.
+__device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys &k, int ptype,
+                                   double vmin, double vmax, const double *__restrict__ inv_d2,
+                                   double *scratch) {
+    double acc = 0.0;
+    auto pts = [&](uint32_t j) { return d[poly_pos(k, j)]; };
+    for (uint32_t x = threadIdx.x; x < k.N; x += blockDim.x) {
+        double v = ptype ? idw_eval_at(k, x, pts, inv_d2) : poly_eval_at(k, x, pts);
+        double out = round_and_limit5(v, vmin, vmax);
+        double o = d[x];
+        acc += fabs(__ddiv_rn(__dsub_rn(out, o), o));
+    }
+    double s = block_sum(acc, scratch);
+    return __ddiv_rn(s, (double)k.N);
+}
+
+// payload size of a Polynomial struct (polynomial.rs:54-87) with K points at `step`
+__device__ inline uint32_t poly_payload_size(const double *__restrict__ d, const PolyKeys &k,
+                                             int bitdepth, bool no_points, uint32_t *scratch) {
+    if (no_points) return 1 + 1 + 1 + 16 + 1;
+    uint32_t vb = 0;
+    if (bitdepth == BD_U8)
+        vb = k.K;
+    else if (bitdepth == BD_F64)
+        vb = 8 * k.K;
+    else {
+        uint32_t loc = 0;
+        for (uint32_t j = threadIdx.x; j < k.K; j += blockDim.x)
+            loc += value_bytes(d[poly_pos(k, j)], bitdepth);
+        vb = block_sum_u32(loc, scratch);
+    }
+    return 1 + 1 + varint_len(k.K) + vb + 16 + 1;
+}
+
+// near-tie detector for `round3(e) < round4(cur)` (polynomial.rs:231,255)
+__device__ inline bool poly_loop_near_tie(double cur, double target) {
+    if (!(cur == cur) || isinf(cur)) return false;
+    double c4 = cur * 10000.0;
+    double fr = c4 - floor(c4);
+    return fabs(fr - 0.5) < 1e-6 && fabs(round(c4) / 10000.0 - target) < 2.5e-4;
+}
+
+// Runs the reference's refinement loop for one frame. All threads of the CTA call.
+// Writes poly_* fields of fw (thread 0).  `sh` = shared scratch (>= 40 doubles).
+__device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, double max_err,
+                                  const double *__restrict__ inv_d2, double *sh) {
+    const uint32_t N = fw->len;
+    const double vmin = fw->vmin, vmax = fw->vmax;
+    const int ptype = fw->poly_type;
+    const int bitdepth = fw->bitdepth;
+    uint32_t step = 1;
+    double cur = 0.0;
+    uint32_t it = 0;
+    bool tie = false;
+    bool no_points = (vmax == vmin);  // polynomial.rs:210,280 "Same max and min"
+    const uint32_t baseline = (3 >= N / 100) ? 3 : N / 100;
+    if (!no_points) {
+        if (!fw->bounded) {
+            // Polynomial::compress (polynomial.rs:307-314)
+            step = N / baseline;
+            if (step < 1) step = 1;
+        } else {
+            cur = max_err + 1.0;
+            uint32_t jump = 0;
+            const double target = round_f64_dec(max_err, 3);
+            uint32_t prev_step = 0;
+            double prev_err = 0.0;
+            while (target < round_f64_dec(cur, 4)) {
+                it++;
+                uint32_t points = baseline + jump;
+                step = N / points;
+                if (step < 1) step = 1;
+                PolyKeys k = poly_keys(N, step);
+                if (step == prev_step) {
+                    cur = prev_err;  // same keys -> same reconstruction -> same error
+                } else if (step == 1 && it <= 22) {
+                    cur = 0.0;  // value unused: the `len == data_len` exit below overrides it
+                } else {
+                    cur = poly_mape(d, k, ptype, vmin, vmax, inv_d2, sh);
+                }
+                prev_step = step;
+                prev_err = cur;
+                tie = tie || poly_loop_near_tie(cur, target);
+                if (it <= 17) {
+                    uint32_t j = N / 10;
+                    jump += j > 1 ? j : 1;
+                } else if (it <= 22) {
+                    uint32_t j = N / 100;
+                    jump += j > 1 ? j : 1;
+                } else if (target > round_f64_dec(cur, 4)) {
+                    break;
+                } else {
+                    step = 1;  // compress_hinted(data, data_len): store everything
+                    cur = 0.0;
+                    break;
+                }
+                if (k.K == N) {
+                    cur = 0.0;
+                    break;
+                }
+            }
+        }
+    }
+    PolyKeys k = poly_keys(N, step);
+    uint32_t size = poly_payload_size(d, k, bitdepth, no_points, (uint32_t *)sh);
+    if (threadIdx.x == 0) {
+        fw->poly_step = step;
+        fw->poly_npts = no_points ? 0 : k.K;
+        fw->poly_size = size;
+        fw->poly_iters = (uint16_t)it;
+        fw->poly_tie = tie ? 1 : 0;
+        fw->poly_err = cur;
+        fw->poly_valid = 1;
+    }
+    __syncthreads();
+}
+
+// Emits the Polynomial payload (polynomial.rs:54-87) at `out`; all threads call.
+// sh: >= 40 uint32 scratch.
+__device__ inline void poly_emit(const double *__restrict__ d, const FrameWork *fw, uint8_t *out,
+                                 uint32_t *sh) {
+    const uint32_t N = fw->len;
+    const int bitdepth = fw->bitdepth;
+    const bool no_points = fw->poly_npts == 0;
+    PolyKeys k = poly_keys(N, fw->poly_step);
+    uint32_t K = no_points ? 0 : k.K;
+    uint32_t hdr = 2 + varint_len(K);
+    if (threadIdx.x == 0) {
+        out[0] = fw->poly_type ? 1 : 0;  // PolynomialType variant (polynomial.rs:29-34)
+        out[1] = (uint8_t)bitdepth;
+        put_varint(out + 2, K);
+    }
+    uint32_t body = 0;
+    if (bitdepth == BD_U8 || bitdepth == BD_F64) {
+        uint32_t w = bitdepth == BD_U8 ? 1 : 8;
+        for (uint32_t j = threadIdx.x; j < K; j += blockDim.x)
+            put_value(out + hdr + (size_t)j * w, d[poly_pos(k, j)], bitdepth);
+        body = K * w;
+    } else {
+        // varint-coded points: tile-wise exclusive scan of byte lengths
+        uint32_t base = 0;
+        for (uint32_t j0 = 0; j0 < K; j0 += blockDim.x) {
+            uint32_t j = j0 + threadIdx.x;
+            double v = j < K ? d[poly_pos(k, j)] : 0.0;
+            uint32_t len = j < K ? value_bytes(v, bitdepth) : 0;
+            uint32_t tot;
+            uint32_t off = block_excl_scan_u32(len, sh, &tot);
+            if (j < K) put_value(out + hdr + base + off, v, bitdepth);
+            base += tot;
+            __syncthreads();
+        }
+        body = base;
+    }
+    if (threadIdx.x == 0) {
+        uint8_t *p = out + hdr + body;
+        double mn = fw->vmin, mx = fw->vmax;
+        put_bytes(p, &mn, 8);
+        put_bytes(p + 8, &mx, 8);
+        p[16] = (uint8_t)fw->poly_step;  // `step as u8`
+    }
+}
+
+}  // namespace atsc

@@ -1,0 +1,58 @@
+"""CPU-side checks of the shipped library: it builds, loads, exports every symbol declared in
+include/atsc_gpu.h, its host-only planner matches the reference tables, and it fails loudly
+(no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import atsc_b200
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "atsc_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(atsc_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = atsc_b200.load_library()
+    syms = declared_symbols()
+    assert set(syms) == set(atsc_b200.API_SYMBOLS)
+    for s in syms:
+        assert getattr(L, s) is not None, s
+
+
+def test_host_planner_matches_reference_tables():
+    # optimizer/mod.rs:150-165
+    assert atsc_b200.chunk_sizes(131072 * 3 + 1765) == [131072, 131072, 131072, 1024, 512, 229]
+    assert atsc_b200.chunk_sizes(31) == [31]
+    assert atsc_b200.chunk_sizes(2048) == [2048]
+    assert atsc_b200.chunk_sizes(12032) == [8192, 2048, 1024, 512, 256]
+    assert atsc_b200.chunk_sizes(0) == []
+    for n in (1, 511, 512, 513, 1000000, 1048576, 65536 + 77):
+        assert atsc_b200.chunk_sizes(n) == O.chunk_sizes(n)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(atsc_b200.AtscError) as ei:
+        atsc_b200.Context()
+    assert ei.value.code == 2  # ATSC_ERR_CUDA
+
+
+def test_product_does_not_touch_the_oracle():
+    """The oracle is test infrastructure: nothing under atsc_b200/ may reference it."""
+    for dp, _, fs in os.walk(os.path.join(ROOT, "atsc_b200")):
+        if "build" in dp.split(os.sep):
+            continue
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in txt.lower() or f == "__init__.py" and "oracle" not in txt.lower(), f
