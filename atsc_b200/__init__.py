@@ -26,8 +26,9 @@ ERRORS = {1: "ATSC_ERR_ARG", 2: "ATSC_ERR_CUDA", 3: "ATSC_ERR_CAPACITY", 4: "ATS
 API_SYMBOLS = [
     "atsc_gpu_create", "atsc_gpu_destroy", "atsc_gpu_last_error", "atsc_gpu_host_alloc", "atsc_gpu_host_free",
     "atsc_gpu_compress_frames", "atsc_gpu_decompress_frames", "atsc_plan_chunk_sizes",
-    "atsc_gpu_compress_series", "atsc_gpu_decompress_series", "atsc_gpu_launch_count",
+    "atsc_gpu_compress_series", "atsc_gpu_decompress_series", "atsc_gpu_launch_count", "atsc_gpu_kernel_ms",
 ]
+KERNEL_NAMES = ["stats", "poly", "rle", "fft", "select", "emit", "decode", "reserved"]
 
 
 class AtscError(RuntimeError):
@@ -78,6 +79,8 @@ def load_library(build_if_missing=True):
     L.atsc_gpu_host_free.argtypes = [vp]
     L.atsc_gpu_launch_count.restype = C.c_uint64
     L.atsc_gpu_launch_count.argtypes = [vp]
+    L.atsc_gpu_kernel_ms.restype = None
+    L.atsc_gpu_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
     L.atsc_gpu_compress_frames.restype = C.c_int
     L.atsc_gpu_compress_frames.argtypes = [vp, vp, u64p, u32p, C.c_uint32, C.c_uint8, C.c_float, C.c_uint32,
                                            C.c_int, C.POINTER(FrameOut), vp, C.c_uint64, u64p]
@@ -140,6 +143,12 @@ class Context:
     def launches(self):
         return int(self.L.atsc_gpu_launch_count(self.h))
 
+    def kernel_ms(self, reset=True):
+        """CUDA-event milliseconds per kernel since the last reset (dict by kernel name)."""
+        arr = (C.c_double * 8)()
+        self.L.atsc_gpu_kernel_ms(self.h, arr, 1 if reset else 0)
+        return {k: arr[i] for i, k in enumerate(KERNEL_NAMES)}
+
     # ------------------------------------------------------------------ frame level (C ABI)
     def compress_frames(self, samples, frame_off, frame_len, compressor=AUTO, max_error=0.05, speed=0,
                         bounded=True, payload_cap=None, samples_ptr=None):
@@ -150,7 +159,7 @@ class Context:
         n = len(fl)
         out = (FrameOut * max(n, 1))()
         if payload_cap is None:
-            payload_cap = int(fl.astype(np.uint64).sum()) * 10 + 64 * n + 64
+            payload_cap = int(fl.astype(np.uint64).sum()) * 16 + 64 * n + 64
         payload = np.empty(payload_cap, dtype=np.uint8)
         used = C.c_uint64()
         if samples_ptr is None:
@@ -226,7 +235,7 @@ class Context:
         flat = np.concatenate(series) if series else np.zeros(0)
         if len(flat) == 0:
             flat = np.zeros(1)
-        cap = int(lens.sum()) * 10 + 4096 * len(series) + 4096
+        cap = int(lens.sum()) * 16 + 4096 * len(series) + 4096
         buf = np.empty(cap, dtype=np.uint8)
         bo = np.zeros(len(series), dtype=np.uint64)
         bl = np.zeros(len(series), dtype=np.uint64)

@@ -56,6 +56,10 @@ struct Device {
     uint32_t *d_status = nullptr, *h_status = nullptr;
     size_t status_cap = 0;
     uint64_t launches = 0;
+    // CUDA-event timing of every kernel on this device's stream (ms accumulated since reset):
+    // 0 stats, 1 plan+poly, 2 rle, 3 fft, 4 noop+select+scan, 5 emit, 6 decode, 7 unused
+    cudaEvent_t ev[10] = {};
+    double ms[8] = {};
     std::string err;
 };
 
@@ -243,6 +247,7 @@ int device_init(Device &D) {
     CK(cudaMalloc((void **)&D.inv_d2, (size_t)(MAX_FRAME + 8) * 8));
     launch_inv_d2(D.inv_d2, MAX_FRAME + 8, D.st);
     D.launches++;
+    for (auto &e : D.ev) CK(cudaEventCreate(&e));
     CK(cudaMalloc((void **)&D.queues, 64 * sizeof(unsigned)));
     CK(cudaMalloc((void **)&D.d_total, 8));
     CK(cudaMallocHost((void **)&D.h_total, 8));
@@ -263,6 +268,8 @@ void device_free(Device &D) {
     void *hp[] = {D.h_total, D.h_frames, D.h_payload, D.h_dec, D.h_status};
     for (void *p : hp)
         if (p) cudaFreeHost(p);
+    for (auto &e : D.ev)
+        if (e) cudaEventDestroy(e);
     if (D.st) cudaStreamDestroy(D.st);
 }
 
@@ -329,11 +336,16 @@ int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &re
     if ((rc = grow(D, D.d_arena, D.arena_cap, (size_t)arena + 1))) return rc;
     CK(cudaMemcpyAsync(D.d_frames, D.h_frames, (size_t)n * sizeof(FrameWork), cudaMemcpyHostToDevice, D.st));
     CK(cudaMemsetAsync(D.queues, 0, 64 * sizeof(unsigned), D.st));
+    CK(cudaEventRecord(D.ev[0], D.st));
     launch_stats(D.d_frames, n, d_samples, D.queues + 0, D.st);
+    CK(cudaEventRecord(D.ev[1], D.st));
     launch_plan(D.d_frames, n, D.st);
     launch_poly(D.d_frames, n, d_samples, max_err, D.inv_d2, D.queues + 1, D.st);
+    CK(cudaEventRecord(D.ev[2], D.st));
     launch_rle(D.d_frames, n, d_samples, max_err, D.pool, D.queues + 2, D.st);
+    CK(cudaEventRecord(D.ev[3], D.st));
     launch_fft(D.d_frames, n, d_samples, max_err, D.geoms_dev, D.pool, D.d_arena, D.queues + 3, D.st);
+    CK(cudaEventRecord(D.ev[4], D.st));
     D.launches += 5;
     if (any_noop) {
         launch_noop_size(D.d_frames, n, d_samples, D.queues + 4, D.st);
@@ -342,21 +354,34 @@ int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &re
     launch_select(D.d_frames, n, max_err, D.st);
     launch_scan(D.d_frames, n, D.d_total, D.st);
     D.launches += 2;
+    CK(cudaEventRecord(D.ev[5], D.st));
     CK(cudaMemcpyAsync(D.h_total, D.d_total, 8, cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
     CK(cudaGetLastError());
+    for (int k = 0; k < 5; k++) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, D.ev[k], D.ev[k + 1]));
+        D.ms[k] += t;
+    }
     uint64_t total = *D.h_total;
     *payload_total = total;
     if (total) {
         if ((rc = grow(D, D.d_payload, D.payload_cap, (size_t)total + 16))) return rc;
         if ((rc = grow(D, D.h_payload, D.h_payload_cap, (size_t)total + 16, true))) return rc;
+        CK(cudaEventRecord(D.ev[6], D.st));
         launch_emit(D.d_frames, n, d_samples, D.geoms_dev, D.pool, D.d_arena, D.d_payload, D.queues + 5, D.st);
+        CK(cudaEventRecord(D.ev[7], D.st));
         D.launches++;
         CK(cudaMemcpyAsync(D.h_payload, D.d_payload, (size_t)total, cudaMemcpyDeviceToHost, D.st));
     }
     CK(cudaMemcpyAsync(D.h_frames, D.d_frames, (size_t)n * sizeof(FrameWork), cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
     CK(cudaGetLastError());
+    if (total) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, D.ev[6], D.ev[7]));
+        D.ms[5] += t;
+    }
     return ATSC_OK;
 }
 
@@ -554,7 +579,9 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
         CK(cudaMemcpyAsync(D.d_pay_in, payloads + plo, (size_t)(phi - plo), cudaMemcpyHostToDevice, D.st));
         CK(cudaMemsetAsync(D.queues, 0, 64 * sizeof(unsigned), D.st));
         double *d_out = out_dev ? out : D.d_out;
+        CK(cudaEventRecord(D.ev[8], D.st));
         launch_decode(D.d_dec, n, D.d_pay_in, d_out, D.geoms_dev, D.pool, D.inv_d2, D.d_status, D.queues + 6, D.st);
+        CK(cudaEventRecord(D.ev[9], D.st));
         D.launches++;
         CK(cudaMemcpyAsync(D.h_status, D.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, D.st));
         if (!out_dev) {
@@ -576,6 +603,11 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
         }
         CK(cudaStreamSynchronize(D.st));
         CK(cudaGetLastError());
+        {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, D.ev[8], D.ev[9]));
+            D.ms[6] += t;
+        }
         for (uint32_t k = 0; k < n; k++)
             if (D.h_status[k]) {
                 char b[128];
@@ -667,6 +699,16 @@ uint64_t atsc_gpu_launch_count(const atsc_ctx *ctx) {
     return n;
 }
 
+void atsc_gpu_kernel_ms(atsc_ctx *ctx, double *out8, int reset) {
+    for (int k = 0; k < 8; k++) out8[k] = 0.0;
+    if (!ctx) return;
+    for (Device *D : ctx->devs)
+        for (int k = 0; k < 8; k++) {
+            out8[k] += D->ms[k];
+            if (reset) D->ms[k] = 0.0;
+        }
+}
+
 int atsc_gpu_compress_frames(atsc_ctx *ctx, const double *samples, const uint64_t *frame_off,
                              const uint32_t *frame_len, uint32_t n_frames, uint8_t compressor, float max_error,
                              uint32_t speed, int bounded, atsc_frame_out *out, uint8_t *payload_buf,
@@ -719,7 +761,7 @@ int atsc_gpu_compress_frames(atsc_ctx *ctx, const double *samples, const uint64_
     std::vector<std::thread> th;
     for (size_t d = 0; d < nd; d++) {
         uint64_t cap = 0;
-        for (uint32_t i : parts[d]) cap += (uint64_t)frame_len[i] * 10 + 64;
+        for (uint32_t i : parts[d]) cap += (uint64_t)frame_len[i] * 16 + 64;  // worst case: RLE of all-distinct f64
         bufs[d].resize(cap);
         sinks[d] = PayloadSink{bufs[d].data(), cap, 0, false};
         th.emplace_back([&, d]() {

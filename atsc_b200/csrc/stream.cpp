@@ -121,7 +121,7 @@ extern "C" int atsc_gpu_compress_series(atsc_ctx *ctx, const double *samples, co
     const float max_error = (float)error_pct / 100.0f;  // `arguments.error as f32 / 100.0`
     std::vector<atsc_frame_out> fo(nf);
     uint64_t pcap = 0;
-    for (uint32_t i = 0; i < nf; i++) pcap += (uint64_t)f_len[i] * 10 + 64;
+    for (uint32_t i = 0; i < nf; i++) pcap += (uint64_t)f_len[i] * 16 + 64;  // worst case: RLE of all-distinct f64
     std::vector<uint8_t> payload(pcap);
     uint64_t pused = 0;
     if (nf) {

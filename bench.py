@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the ATSC hot path on B200 (contract: see the task statement).
+
+Workload (config.workload): BASELINE.json config 4 ("auto selection at -c 0 ... mixed
+constant/periodic/noisy") scaled to one GPU: S series x 1,000,000 samples per GPU, one third
+constant, one third periodic (SURVEY.md C2 formula, sigma 0.05), one third noisy (C3 class b
+utilisation gauge), `atsc --compressor auto -e 5 -c 0`; the 100k x 1M fleet of the config is
+800 GB and does not fit, so each GPU processes a stated subsample per step (weak scaling: the
+per-GPU share is fixed as N grows, frames never communicate, no collective).
+
+One "step" = one pass of the hot path over the GPU's whole batch:
+  value   : Msamples/s, inputs resident in HBM when the clock starts, payloads + frame
+            records copied back to the host inside the timed region.
+  e2e     : same call with the samples in pinned HOST memory (H2D inside the timed region).
+  roofline: dominant kernel (k_fft) -- algorithmic bytes = 8 B x samples of the frames it
+            transforms / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline: the oracle port (C restatement of the reference) on the host cores, bounded sample.
+  decompress: GB/s of f64 output for the BRO fleet produced by the compress step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SERIES_LEN = 1_000_000
+ERROR_PCT = 5
+SPEED = 0
+
+
+def make_series(cls, seed):
+    import gen
+    if cls == 0:
+        return gen.constant(SERIES_LEN, seed)
+    if cls == 1:
+        return gen.periodic(SERIES_LEN, seed, sigma=0.05)
+    return gen.utilisation(SERIES_LEN, seed)
+
+
+def make_fleet(n_series, seed0, out):
+    """Fills out[n_series, SERIES_LEN] with the mixed fleet (class = series index mod 3)."""
+    for s in range(n_series):
+        out[s, :] = make_series(s % 3, seed0 + s)
+
+
+def frame_table(n_series):
+    import atsc_b200
+    cs = atsc_b200.chunk_sizes(SERIES_LEN)
+    offs, lens = [], []
+    for s in range(n_series):
+        o = s * SERIES_LEN
+        for c in cs:
+            offs.append(o)
+            lens.append(c)
+            o += c
+    return np.array(offs, dtype=np.uint64), np.array(lens, dtype=np.uint32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.rows = []
+        self.stop = False
+        self.th = None
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for nm, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(threads, budget_s=20.0):
+    """Oracle port timed on the host cores on a bounded sample of the same workload."""
+    import oracle_lib as O
+    O.lib()
+    per_class = max(1, threads // 3)
+    n = per_class * 3
+    arr = np.empty((n, SERIES_LEN))
+    make_fleet(n, 5000, arr)
+    t0 = time.perf_counter()
+    O.compress_batch(arr, O.AUTO, ERROR_PCT, SPEED, threads)
+    dt = time.perf_counter() - t0
+    reps = 1
+    # repeat while cheap so the figure is not a single noisy shot
+    while dt * (reps + 1) / reps < budget_s and reps < 3:
+        t1 = time.perf_counter()
+        O.compress_batch(arr, O.AUTO, ERROR_PCT, SPEED, threads)
+        dt = min(dt, time.perf_counter() - t1)
+        reps += 1
+    return {"value": n * SERIES_LEN / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
+            "sample": f"{n} series x {SERIES_LEN} samples ({per_class} per class), best of {reps}, "
+                      f"{threads} threads, one series per thread at a time (reference is single-threaded per series)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Rust
+    reference cannot be built in this image) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle_lib as O
+    O.lib()
+    threads = os.cpu_count() or 1
+    per_class = max(1, threads // 3)
+    n = per_class * 3
+    arr = np.empty((n, SERIES_LEN))
+    make_fleet(n, 5000, arr)
+    for _ in range(args.warmup):
+        O.compress_batch(arr[:3], O.AUTO, ERROR_PCT, SPEED, min(3, threads))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.compress_batch(arr, O.AUTO, ERROR_PCT, SPEED, threads)
+    dt = time.perf_counter() - t0
+    v = args.steps * n * SERIES_LEN / dt / 1e6
+    sample = f"{n} series x {SERIES_LEN} samples per step ({per_class} per class), {threads} threads"
+    line = {
+        "impl": "reference", "metric": "auto_compress_msamples_per_s", "value": v, "unit": "Msamples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
+        "config": workload_config(n, 1),
+        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(series_per_gpu, n_gpus):
+    return {
+        "workload": f"atsc --compressor auto -e {ERROR_PCT} -c {SPEED}: {series_per_gpu} series/GPU x {SERIES_LEN} samples "
+                    "(1/3 constant, 1/3 periodic sigma=0.05, 1/3 noisy utilisation gauge), "
+                    "frames [131072x7,65536,16384,512,64] per series; subsample of BASELINE config 4 (100k x 1M)",
+        "series_per_gpu": series_per_gpu, "series_len": SERIES_LEN, "error_pct": ERROR_PCT, "speed": SPEED,
+        "parallelism": f"frames sharded by series over {n_gpus} GPU(s), no collective",
+        "l2_policy": "inputs (>= 768 MB per GPU) exceed the 126 MB L2",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--series", type=int, default=96, help="series per GPU (multiple of 3)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import atsc_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warmup = max(args.warmup, 3)
+    S = args.series
+    ctx = atsc_b200.Context([local])
+    L = ctx.L
+
+    # ---- inputs: pinned host fleet (for e2e) + device copy (for value)
+    nbytes = S * SERIES_LEN * 8
+    hptr = L.atsc_gpu_host_alloc(nbytes)
+    import ctypes as C
+    host = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_double)), shape=(S, SERIES_LEN))
+    make_fleet(S, 5000 + rank * S, host)
+    dev = torch.empty(S * SERIES_LEN, dtype=torch.float64, device="cuda")
+    dev.copy_(torch.from_numpy(host.reshape(-1)))
+    torch.cuda.synchronize()
+    offs, lens = frame_table(S)
+    n_samples = S * SERIES_LEN
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        return ctx.compress_frames(None, offs, lens, atsc_b200.AUTO, ERROR_PCT / 100.0, SPEED, True,
+                                   samples_ptr=dev.data_ptr())
+
+    def step_host():
+        return ctx.compress_frames(host.reshape(-1), offs, lens, atsc_b200.AUTO, ERROR_PCT / 100.0, SPEED, True)
+
+    def timed(fn, steps):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = fn()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, r
+
+    for _ in range(warmup):
+        out, payload = step_dev()
+    ctx.kernel_ms(reset=True)
+    l0 = ctx.launches
+    with ClockSampler(local) as clk:
+        dt, (out, payload) = timed(step_dev, args.steps)
+    launches = ctx.launches - l0
+    kms = ctx.kernel_ms(reset=True)
+    value = world * n_samples * args.steps / dt / 1e6
+
+    # ---- e2e: host buffers, H2D inside
+    for _ in range(2):
+        step_host()
+    dt_e2e, _ = timed(step_host, args.steps)
+    e2e_v = world * n_samples * args.steps / dt_e2e / 1e6
+    d2h = int(len(payload)) + len(lens) * 168
+
+    # ---- roofline of the dominant kernel
+    comps = np.array([out[i].compressor for i in range(len(lens))])
+    nonconst = comps != atsc_b200.CONSTANT
+    fft_samples = int(lens[nonconst].astype(np.int64).sum())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom = max(("stats", "poly", "rle", "fft", "select", "emit"), key=lambda k: kms[k])
+    dom_ms = kms[dom] / args.steps
+    dom_samples = n_samples if dom in ("stats", "select") else fft_samples
+    achieved = dom_samples * 8 / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items() if v},
+                "whole_step_frac": n_samples * 8 / (dt / args.steps) / 1e9 / peak,
+                "note": "k_fft is FP32/shared-memory bound (<=24 length-139968 transforms per noisy frame); "
+                        "the HBM line is the task's stated denominator"}
+
+    # ---- decompression of the fleet just produced (device-resident output)
+    frames_in, po = [], 0
+    oo = 0
+    for i in range(len(lens)):
+        o = out[i]
+        frames_in.append((o.compressor, int(lens[i]), int(o.payload_off), int(o.payload_len), oo))
+        oo += int(lens[i])
+    dout = torch.empty(n_samples, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        ctx.decompress_frames(frames_in, payload, out_ptr=dout.data_ptr())
+    ctx.kernel_ms(reset=True)
+    dt_dec, _ = timed(lambda: ctx.decompress_frames(frames_in, payload, out_ptr=dout.data_ptr()), args.steps)
+    dec_ms = ctx.kernel_ms(reset=True)["decode"] / args.steps
+    hout = np.empty(n_samples)
+    dt_dec_e2e, _ = timed(lambda: ctx.decompress_frames(frames_in, payload, out=hout), max(1, args.steps // 2))
+    dec = {"value": world * n_samples * 8 * args.steps / dt_dec / 1e9, "unit": "GB/s (f64 out)",
+           "kernel_gbs": n_samples * 8 / (dec_ms * 1e-3) / 1e9 if dec_ms else None,
+           "kernel_frac_of_hbm_peak": (n_samples * 8 / (dec_ms * 1e-3) / 1e9 / peak) if dec_ms else None,
+           "e2e_gbs": world * n_samples * 8 * max(1, args.steps // 2) / dt_dec_e2e / 1e9,
+           "payload_bytes": int(len(payload))}
+
+    # ---- sanity: the timed result is a real compress (sizes, winners)
+    names = atsc_b200.COMPRESSOR_NAMES
+    hist = {names[c]: int((comps == c).sum()) for c in np.unique(comps)}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_baseline(os.cpu_count() or 1)
+        line = {
+            "metric": "auto_compress_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (stats/poly/rle/error) + f32 (fft, as the reference)",
+            "data": "synthetic", "config": workload_config(S, world),
+            "e2e": {"value": e2e_v, "unit": "Msamples/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "decompress": dec,
+            "clocks": clk.summary(), "winners": hist, "compressed_bytes": int(len(payload)),
+            "compression_ratio": n_samples * 8 / max(1, len(payload)),
+        }
+        print(json.dumps(line))
+    L.atsc_gpu_host_free(hptr)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -150,6 +150,11 @@ int atsc_gpu_decompress_series(atsc_ctx *ctx, const uint8_t *bro_buf, const uint
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t atsc_gpu_launch_count(const atsc_ctx *ctx);
 
+/* CUDA-event time (ms, summed over devices, accumulated since the last reset) of each kernel
+ * on the library's own streams: [0] stats [1] plan+polynomial [2] rle [3] fft
+ * [4] noop-size+select+scan [5] emit [6] decode [7] reserved */
+void atsc_gpu_kernel_ms(atsc_ctx *ctx, double *out8, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,7 +96,7 @@ def _f64(x):
 
 
 def _cap(n):
-    return int(n) * 12 + 4096
+    return int(n) * 16 + 4096
 
 
 def next_size(n):
