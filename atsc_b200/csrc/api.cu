@@ -33,6 +33,7 @@ struct Device {
     unsigned long long *d_total = nullptr, *h_total = nullptr;
     // geometry cache
     std::map<uint32_t, int> geom_idx;
+    std::map<uint32_t, uint32_t> pad_cache;
     std::vector<FftGeom> geoms_host;
     std::vector<void *> geom_allocs;
     FftGeom *geoms_dev = nullptr;
@@ -197,6 +198,16 @@ int get_geom(Device &D, uint32_t L, int *out_idx) {
     return ATSC_OK;
 }
 
+// next_size (utils/mod.rs:32-38) memoised per frame length: the search loop costs tens of
+// microseconds for 131072 and would otherwise run once per frame
+uint32_t padded_len(Device &D, uint32_t len) {
+    auto it = D.pad_cache.find(len);
+    if (it != D.pad_cache.end()) return it->second;
+    uint32_t L = (uint32_t)atsc_host::next_size(len);
+    D.pad_cache[len] = L;
+    return L;
+}
+
 int sync_geoms(Device &D) {
     if (!D.geoms_dirty) return ATSC_OK;
     int rc = grow(D, D.geoms_dev, D.geoms_dev_cap, D.geoms_host.size() + 8);
@@ -315,7 +326,7 @@ int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &re
         uint8_t eff = (r.comp == C_AUTO && r.forced != 0xFF) ? r.forced : r.comp;
         any_noop |= r.comp == C_NOOP;
         if (eff == C_FFT || eff == C_AUTO) {
-            uint32_t L = (r.bounded && r.len >= 128) ? (uint32_t)atsc_host::next_size(r.len) : r.len;
+            uint32_t L = (r.bounded && r.len >= 128) ? padded_len(D, r.len) : r.len;
             if (r.len >= 128) {
                 int gi;
                 if ((rc = get_geom(D, L, &gi))) {
@@ -570,7 +581,7 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
             }
             if (f.compressor == C_FFT && f.sample_count >= 128) {
                 int gi;
-                if ((rc = get_geom(D, (uint32_t)atsc_host::next_size(f.sample_count), &gi))) return rc;
+                if ((rc = get_geom(D, padded_len(D, f.sample_count), &gi))) return rc;
                 d.geom = gi;
             }
         }
