@@ -174,6 +174,9 @@ int get_geom(Device &D, uint32_t L, int *out_idx) {
         r.y = (float)(-std::sin(a));
         return r;
     };
+    std::vector<float2> twL1(g.M1), twL2(g.M2);
+    for (uint32_t j = 0; j < g.M1; j++) twL1[j] = root(j, L);
+    for (uint32_t j = 0; j < g.M2; j++) twL2[j] = root((double)j * g.M1, L);
     std::vector<float2> twM(g.M), tw1(g.M1), tw2(g.M2), twL(g.M + 1), twA((size_t)g.M1 * 32), twB((size_t)g.M2 * 32);
     for (uint32_t j = 0; j < g.M; j++) twM[j] = root(j, g.M);
     for (uint32_t j = 0; j < g.M1; j++) tw1[j] = root(j, g.M1);
@@ -188,6 +191,8 @@ int get_geom(Device &D, uint32_t L, int *out_idx) {
     if ((rc = upload_vec(D, tw1, &g.tw1))) return rc;
     if ((rc = upload_vec(D, tw2, &g.tw2))) return rc;
     if ((rc = upload_vec(D, twL, &g.twL))) return rc;
+    if ((rc = upload_vec(D, twL1, &g.twL1))) return rc;
+    if ((rc = upload_vec(D, twL2, &g.twL2))) return rc;
     if ((rc = upload_vec(D, twA, &g.twA))) return rc;
     if ((rc = upload_vec(D, twB, &g.twB))) return rc;
     int idx = (int)D.geoms_host.size();

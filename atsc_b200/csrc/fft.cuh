@@ -32,6 +32,8 @@ struct FftGeom {
     const float2 *tw1;  // exp(-2 pi i j / M1)
     const float2 *tw2;  // exp(-2 pi i j / M2)
     const float2 *twL;  // exp(-2 pi i j / L), j <= M
+    const float2 *twL1; // exp(-2 pi i k1 / L), k1 < M1
+    const float2 *twL2; // exp(-2 pi i M1 k2 / L), k2 < M2
     const float2 *twA;  // [M1][32]: exp(-2 pi i e f / M)
     const float2 *twB;  // [M2][32]
 };
@@ -71,8 +73,14 @@ __device__ inline float2 *tile_fft(float2 *x, float2 *y, int len, const uint8_t 
         const int nbf = len / r;
         const int tws = len / n;
         if (lane < nb) {
-            for (int b = warp; b < nbf; b += nw) {
-                const int p = b / s, q = b - p * s;
+            // butterfly b = p * s + q; advance (p, q) incrementally instead of dividing per butterfly
+            int p = warp / s, q = warp - p * s;
+            const int dp = nw / s, dq = nw - dp * s;
+            for (int b = warp; b < nbf; b += nw, p += dp, q += dq) {
+                if (q >= s) {
+                    q -= s;
+                    p++;
+                }
                 const float2 *xi = x + (q + s * p) * FFT_FP + lane;
                 float2 *yo = y + (q + s * r * p) * FFT_FP + lane;
                 const int xs = s * m * FFT_FP;  // input stride between radix legs
@@ -212,103 +220,145 @@ __device__ inline void fft_forward(const double *__restrict__ d, uint32_t N, uin
     }
     __threadfence_block();
     __syncthreads();
-    // post-process: X[k] for k = 0..L/2 in natural order + |X[k]| keys
+    // post-process: half spectrum X[k], k = 0..L/2, and its |X[k]| keys.
+    // Real-input trick: entries are produced in *storage* order i = k1*M2 + k2 (k = k1 + M1*k2) so
+    // both Z[k] and its partner Z[M-k] are read with unit stride; entry M holds the Nyquist bin.
+    // Odd L: natural order (only the two small odd lengths 243 / 2187 take this path).
     const uint32_t M = g.M;
-    for (uint32_t k = threadIdx.x; k < g.Bn; k += blockDim.x) {
-        float2 X;
-        if (g.real) {
-            uint32_t ka = k % M, kb = (M - k) % M;
-            float2 Zk = ws.W[(size_t)(ka % M1) * M2 + ka / M1];
-            float2 Zm = ws.W[(size_t)(kb % M1) * M2 + kb / M1];
-            Zm.y = -Zm.y;  // conj
-            float2 sum = cadd(Zk, Zm), dif = csub(Zk, Zm);
-            float2 t = cmul(g.twL[k], dif);  // twL * (Zk - conj Zmk)
-            // X = 0.5 * (sum - i * t)
-            X.x = 0.5f * (sum.x + t.y);
-            X.y = 0.5f * (sum.y - t.x);
-        } else {
-            X = ws.W[(size_t)(k % M1) * M2 + k / M1];
+    if (g.real) {
+        for (uint32_t i = threadIdx.x; i <= M; i += blockDim.x) {
+            float2 X;
+            if (i == M) {
+                float2 Z0 = ws.W[0];
+                X = make_float2(Z0.x - Z0.y, 0.f);  // X[M] = Re Z0 - Im Z0
+            } else {
+                uint32_t k1 = i / (uint32_t)M2, k2 = i - k1 * (uint32_t)M2;
+                float2 Zk = ws.W[i];
+                // partner M-k: (M1-k1, M2-1-k2) for k1 > 0, (0, M2-k2) for k1 == 0 < k2, itself for k == 0
+                uint32_t pi = k1 ? (M1 - k1) * (uint32_t)M2 + ((uint32_t)M2 - 1 - k2) : (k2 ? (uint32_t)M2 - k2 : 0u);
+                float2 Zm = ws.W[pi];
+                Zm.y = -Zm.y;  // conj
+                float2 sum = cadd(Zk, Zm), dif = csub(Zk, Zm);
+                float2 w = cmul(g.twL1[k1], g.twL2[k2]);  // exp(-2 pi i (k1 + M1 k2) / L)
+                float2 tt = cmul(w, dif);
+                // X = 0.5 * (sum - i * tt)
+                X.x = 0.5f * (sum.x + tt.y);
+                X.y = 0.5f * (sum.y - tt.x);
+            }
+            ws.Xd[i] = X;
+            // Complex<f32>::norm() == hypotf; via f64 sqrt to stay correctly rounded
+            double nr = sqrt((double)X.x * (double)X.x + (double)X.y * (double)X.y);
+            ws.keys[i] = __float_as_uint((float)nr);
         }
-        ws.Xd[k] = X;
-        // Complex<f32>::norm() == hypotf; via f64 sqrt to stay correctly rounded
-        double nr = sqrt((double)X.x * (double)X.x + (double)X.y * (double)X.y);
-        ws.keys[k] = __float_as_uint((float)nr);
+    } else {
+        for (uint32_t k = threadIdx.x; k < g.Bn; k += blockDim.x) {
+            float2 X = ws.W[(size_t)(k % M1) * M2 + k / M1];
+            ws.Xd[k] = X;
+            double nr = sqrt((double)X.x * (double)X.x + (double)X.y * (double)X.y);
+            ws.keys[k] = __float_as_uint((float)nr);
+        }
     }
     __syncthreads();
 }
 
+// array index of ws.Xd / ws.keys -> spectrum bin (see fft_forward)
+__device__ inline uint32_t fft_bin_of(uint32_t i, uint32_t pM, uint32_t pM1, uint32_t pM2) {
+    if (pM == 0 || i >= pM) return i;
+    uint32_t k1 = i / pM2;
+    return k1 + pM1 * (i - k1 * pM2);
+}
+
 // ---------------------------------------------------------------------------------------
 // top-K of the half spectrum by |z| (fft.rs:231-257), descending, ties by lower bin.
-// Writes list[0..K) and returns K = min(kmax, #nonzero bins).
+// Writes list[0..K) and returns K = min(kmax, #nonzero bins).  (pM, pM1, pM2) describe the
+// storage order of ws.keys (pM = 0: natural order).  sm64 must hold next_pow2(K) u64.
 // ---------------------------------------------------------------------------------------
 __device__ inline uint32_t fft_topk(uint32_t Bn, FftWs ws, uint32_t kmax, FftEntry *list,
-                                    unsigned long long *sm64, uint32_t *sh, bool *tie_at_cut) {
+                                    unsigned long long *sm64, uint32_t *sh, bool *tie_at_cut,
+                                    uint32_t pM, uint32_t pM1, uint32_t pM2) {
     const uint32_t T = blockDim.x, t = threadIdx.x;
     uint32_t *hist = (uint32_t *)sm64;  // 256 bins (phase-local reuse of the big smem region)
-    // number of non-zero bins
-    uint32_t loc = 0;
-    for (uint32_t b = t; b < Bn; b += T) loc += ws.keys[b] != 0u;
-    uint32_t nnz = block_sum_u32(loc, sh);
-    uint32_t K = min(min(kmax, nnz), (uint32_t)FFT_KCAP);
     *tie_at_cut = false;
-    if (K == 0) return 0;
-    // radix select the K-th largest key
-    uint32_t prefix = 0, remaining = K;
+    // radix select the K-th largest key, 8 bits per level; level 0 also counts zero bins
+    uint32_t prefix = 0, remaining = 0, K = 0, eq_total = 0;
     for (int shift = 24; shift >= 0; shift -= 8) {
         for (uint32_t i = t; i < 256; i += T) hist[i] = 0;
         __syncthreads();
+        uint32_t zeros = 0;
         for (uint32_t b = t; b < Bn; b += T) {
             uint32_t key = ws.keys[b];
+            zeros += key == 0u;
             bool in = shift == 24 ? true : (key >> (shift + 8)) == prefix;
             if (in) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
+        if (shift == 24) {
+            uint32_t nz = Bn - block_sum_u32(zeros, sh);
+            K = min(min(kmax, nz), (uint32_t)FFT_KCAP);
+            if (K == 0) return 0;
+            remaining = K;
+        }
         __syncthreads();
-        if (t == 0) {
-            uint32_t acc = 0;
-            int dsel = 0;
-            for (int dgt = 255; dgt >= 0; dgt--) {
-                if (acc + hist[dgt] >= remaining) {
-                    dsel = dgt;
-                    break;
-                }
-                acc += hist[dgt];
-            }
-            sh[102] = (uint32_t)dsel;
-            sh[103] = acc;
+        // digit d is selected when  #(keys with a larger digit) < remaining <= that + hist[d]
+        uint32_t hv = t < 256 ? hist[255 - t] : 0u;
+        uint32_t tot;
+        uint32_t above = block_excl_scan_u32(hv, sh, &tot);
+        if (t < 256 && above < remaining && remaining <= above + hv) {
+            sh[102] = 255 - t;
+            sh[103] = above;
+            sh[106] = hv;
         }
         __syncthreads();
         prefix = (prefix << 8) | sh[102];
         remaining -= sh[103];
+        eq_total = sh[106];
         __syncthreads();
     }
     const uint32_t Tkey = prefix;       // K-th largest key
-    const uint32_t take_eq = remaining;  // how many bins with key == Tkey are taken (lowest bins first)
-    // ordered compaction into composite sort keys
+    const uint32_t take_eq = remaining;  // how many bins with key == Tkey are taken (lowest index first)
+    const bool tie = eq_total > take_eq;
     uint32_t P = 1;
     while (P < K) P <<= 1;
     unsigned long long *S = sm64;
     __syncthreads();
-    uint32_t base = 0, eqbase = 0, eq_total = 0;
-    for (uint32_t b0 = 0; b0 < Bn; b0 += T) {
-        uint32_t b = b0 + t;
-        uint32_t key = b < Bn ? ws.keys[b] : 0u;
-        bool gt = b < Bn && key > Tkey;
-        bool eq = b < Bn && key == Tkey;
-        uint32_t eqtot;
-        uint32_t eqrank = eqbase + block_excl_scan_u32(eq ? 1u : 0u, sh, &eqtot);
+    if (!tie) {
+        // every key >= Tkey is taken: unordered compaction (the sort fixes the order)
+        if (t == 0) sh[107] = 0;
         __syncthreads();
-        bool sel = gt || (eq && eqrank < take_eq);
-        uint32_t tot;
-        uint32_t pos = base + block_excl_scan_u32(sel ? 1u : 0u, sh, &tot);
-        if (sel) S[pos] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - b);
-        base += tot;
-        eqbase += eqtot;
-        eq_total += eqtot;
+        for (uint32_t b = t; b < Bn; b += T) {
+            uint32_t key = ws.keys[b];
+            if (key >= Tkey && key != 0u) {
+                uint32_t pos = atomicAdd(&sh[107], 1u);
+                uint32_t bin = fft_bin_of(b, pM, pM1, pM2);
+                if (pos < P) S[pos] = ((unsigned long long)key << 32) | ((unsigned long long)(0xFFFFFu - bin) << 12) | 0ull;
+            }
+        }
         __syncthreads();
+    } else {
+        // equal |z| straddle the cut: take the lowest array indices first (ordered compaction)
+        uint32_t base = 0, eqbase = 0;
+        for (uint32_t b0 = 0; b0 < Bn; b0 += T) {
+            uint32_t b = b0 + t;
+            uint32_t key = b < Bn ? ws.keys[b] : 0u;
+            bool gt = b < Bn && key > Tkey;
+            bool eq = b < Bn && key == Tkey;
+            uint32_t eqtot;
+            uint32_t eqrank = eqbase + block_excl_scan_u32(eq ? 1u : 0u, sh, &eqtot);
+            __syncthreads();
+            bool sel = gt || (eq && eqrank < take_eq);
+            uint32_t tot;
+            uint32_t pos = base + block_excl_scan_u32(sel ? 1u : 0u, sh, &tot);
+            if (sel) {
+                uint32_t bin = fft_bin_of(b, pM, pM1, pM2);
+                S[pos] = ((unsigned long long)key << 32) | ((unsigned long long)(0xFFFFFu - bin) << 12);
+            }
+            base += tot;
+            eqbase += eqtot;
+            __syncthreads();
+        }
     }
     for (uint32_t i = K + t; i < P; i += T) S[i] = 0ull;
     __syncthreads();
-    // bitonic sort, descending
+    // bitonic sort, descending: (|z| desc, bin asc)
     for (uint32_t k2 = 2; k2 <= P; k2 <<= 1) {
         for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
             for (uint32_t i = t; i < P; i += T) {
@@ -326,15 +376,18 @@ __device__ inline uint32_t fft_topk(uint32_t Bn, FftWs ws, uint32_t kmax, FftEnt
         }
     }
     for (uint32_t r = t; r < K; r += T) {
-        uint32_t bin = 0xFFFFFFFFu - (uint32_t)(S[r] & 0xFFFFFFFFull);
-        float2 X = ws.Xd[bin];
+        uint32_t bin = 0xFFFFFu - (uint32_t)((S[r] >> 12) & 0xFFFFFull);
+        // array index of this bin (inverse of fft_bin_of)
+        uint32_t i = bin;
+        if (pM && bin < pM) i = (bin % pM1) * pM2 + bin / pM1;
+        float2 X = ws.Xd[i];
         FftEntry e;
         e.bin = bin;
         e.re = X.x;
         e.im = X.y;
         list[r] = e;
     }
-    *tie_at_cut = eq_total > take_eq;
+    *tie_at_cut = tie;
     __syncthreads();
     return K;
 }

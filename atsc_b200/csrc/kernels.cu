@@ -198,21 +198,34 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
     const bool alias = Bn > 65536u;
     bool tie_cut;
     unsigned long long *S = (unsigned long long *)sm;
-    const uint32_t K = fft_topk(Bn, ws, min(kmax, fw->fft_list_cap), list, S, sh, &tie_cut);
-    // which schedule cuts split equal |z| (BinaryHeap pop order among equals is unspecified)
-    if (t == 0) {
-        uint32_t mask = 0, jump = 0;
-        for (int it = 1; it <= FFT_SCHED; it++) {
-            uint32_t c = min(mf + jump, K);
-            if (fft_cut_splits_tie(S, c, K) || (c == K && tie_cut && mf + jump >= K && K < Bn)) mask |= 1u << (it - 1);
-            jump += it <= 17 ? hstep : tstep;
-            if (!bounded) break;
+    const uint32_t pM = (gi >= 0 && sg->real) ? sg->M : 0u, pM1 = gi >= 0 ? sg->M1 : 1u, pM2 = gi >= 0 ? sg->M2 : 1u;
+    const uint32_t kcap = min(kmax, fw->fft_list_cap);
+    uint32_t K = 0, cutmask = 0;
+    bool list_full = false;
+    // Builds the sorted list of the `want` largest bins (a prefix of the full list: the order
+    // is deterministic), the per-entry scatter coefficients, and the mask of schedule cuts that
+    // split equal |z| (BinaryHeap pop order among equals is unspecified -> near-tie flag).
+    auto build_list = [&](uint32_t want) {
+        K = fft_topk(Bn, ws, want, list, S, sh, &tie_cut, pM, pM1, pM2);
+        list_full = (want >= kcap) || (K < want);
+        if (t == 0) {
+            uint32_t mask = 0, jump = 0;
+            for (int it = 1; it <= FFT_SCHED; it++) {
+                uint32_t c = min(mf + jump, K);
+                if (fft_cut_splits_tie(S, c, K) || (c == K && tie_cut && mf + jump == K)) mask |= 1u << (it - 1);
+                jump += it <= 17 ? hstep : tstep;
+                if (!bounded || mf + jump > K) break;
+            }
+            sh[105] = mask;
         }
-        sh[105] = mask;
-    }
-    __syncthreads();
-    const uint32_t cutmask = sh[105];
-    __syncthreads();
+        __syncthreads();
+        cutmask |= sh[105];
+        __syncthreads();
+        if (bounded && gi >= 0) fft_prepare_entries(*sg, ws, list, K, alias);
+    };
+    // most frames stop after one or two refinement iterations: sort only the first two schedule
+    // points' worth of bins up front, the full list (<= 16384 entries) only when needed
+    build_list(bounded ? min(mf + hstep, kcap) : kcap);
 
     auto nsmall = [&](uint32_t c) -> uint32_t {
         uint32_t loc = 0;
@@ -236,8 +249,6 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
         }
         return;
     }
-
-    if (gi >= 0) fft_prepare_entries(*sg, ws, list, K, alias);
 
     // a later candidate can only lose to FFT on size; FFT wins ties (frame/mod.rs:77,104,141)
     uint32_t bound = 0xFFFFFFFFu;
@@ -284,6 +295,7 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
     bool pruned = false, tie = false, tie_topk = false;
     while (E < rust_as_i32(cur * 1000.0)) {
         it++;
+        if (!list_full && mf + jump > K) build_list(kcap);
         c = min(mf + jump, K);
         if (bound != 0xFFFFFFFFu) {
             uint32_t ns = nsmall(c);
