@@ -104,8 +104,9 @@ int grow(Device &D, T *&p, size_t &cap, size_t need, bool pinned_host = false) {
 }
 
 // ---------------------------------------------------------------- FFT geometry tables
-void radices_of(uint32_t n, uint8_t *rad, uint32_t *ns) {
-    uint32_t k = 0;
+void radices_of(uint32_t len, FftStage *stg, uint32_t *ns) {
+    uint8_t rad[16];
+    uint32_t k = 0, n = len;
     while (n % 4 == 0) {
         rad[k++] = 4;
         n /= 4;
@@ -119,6 +120,22 @@ void radices_of(uint32_t n, uint8_t *rad, uint32_t *ns) {
         n /= 3;
     }
     *ns = k;
+    uint32_t cur = len, s = 1;
+    const uint32_t nw = BLOCK / 32;
+    for (uint32_t i = 0; i < k; i++) {
+        FftStage &S = stg[i];
+        S.r = rad[i];
+        S.m = (uint16_t)(cur / rad[i]);
+        S.s = (uint16_t)s;
+        S.tws = (uint16_t)(len / cur);
+        S.nbf = (uint16_t)(len / rad[i]);
+        S.dp = (uint16_t)(nw / s);
+        S.dq = (uint16_t)(nw % s);
+        S.pad = 0;
+        S.magic = (65536u + s - 1) / s;
+        cur /= rad[i];
+        s *= rad[i];
+    }
 }
 
 template <class T>
@@ -164,8 +181,8 @@ int get_geom(Device &D, uint32_t L, int *out_idx) {
     if (!b1) return ATSC_ERR_UNSUPPORTED;
     g.M1 = b1;
     g.M2 = b2;
-    radices_of(g.M1, g.rad1, &g.ns1);
-    radices_of(g.M2, g.rad2, &g.ns2);
+    radices_of(g.M1, g.st1, &g.ns1);
+    radices_of(g.M2, g.st2, &g.ns2);
     const double PI2 = 6.283185307179586476925286766559;
     auto root = [&](double num, double den) {
         double a = PI2 * num / den;
@@ -256,6 +273,10 @@ int device_init(Device &D) {
     CK(cudaMalloc((void **)&P.fft_cD, fs * FFT_DEC_KCAP * sizeof(float2)));
     CK(cudaMalloc((void **)&P.fft_cM, fs * FFT_DEC_KCAP * sizeof(float2)));
     CK(cudaMalloc((void **)&P.fft_dlist, fs * FFT_DEC_KCAP * sizeof(FftEntry)));
+    CK(cudaMalloc((void **)&P.fft_w, fs * (MAX_FRAME + 8) * 8));
+    P.poly_slots = 2 * sms;
+    CK(cudaMalloc((void **)&P.poly_slope, (size_t)P.poly_slots * (MAX_FRAME + 8) * 8));
+    CK(cudaMalloc((void **)&P.poly_w, (size_t)P.poly_slots * (MAX_FRAME + 8) * 8));
     size_t dsl = (size_t)P.dec_slots;
     CK(cudaMalloc((void **)&P.dec_pts, dsl * (MAX_FRAME + 8) * 8));
     CK(cudaMalloc((void **)&P.dec_mark, dsl * (MAX_FRAME + 8) * 4));
@@ -275,7 +296,7 @@ void device_free(Device &D) {
     cudaSetDevice(D.id);
     SlotPool &P = D.pool;
     void *ptrs[] = {P.rle_k0, P.rle_k1, P.rle_i0, P.rle_i1, P.rle_bnd, P.fft_W, P.fft_Xd, P.fft_keys, P.fft_rank,
-                    P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.dec_pts, P.dec_mark,
+                    P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.fft_w, P.poly_slope, P.poly_w, P.dec_pts, P.dec_mark,
                     P.dec_idx, D.inv_d2, D.queues, D.d_total, D.geoms_dev, D.d_frames, D.d_samples, D.d_arena,
                     D.d_payload, D.d_dec, D.d_pay_in, D.d_out, D.d_status};
     for (void *p : ptrs)
@@ -356,7 +377,7 @@ int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &re
     launch_stats(D.d_frames, n, d_samples, D.queues + 0, D.st);
     CK(cudaEventRecord(D.ev[1], D.st));
     launch_plan(D.d_frames, n, D.st);
-    launch_poly(D.d_frames, n, d_samples, max_err, D.inv_d2, D.queues + 1, D.st);
+    launch_poly(D.d_frames, n, d_samples, max_err, D.inv_d2, D.pool, D.queues + 1, D.st);
     CK(cudaEventRecord(D.ev[2], D.st));
     launch_rle(D.d_frames, n, d_samples, max_err, D.pool, D.queues + 2, D.st);
     CK(cudaEventRecord(D.ev[3], D.st));

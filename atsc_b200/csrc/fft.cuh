@@ -24,10 +24,18 @@ constexpr int FFT_KCAP = 16384;                                 // max list entr
 constexpr int FFT_DEC_KCAP = 65536;                             // max entries accepted when decoding (pos is a u16)
 constexpr int FFT_SCHED = 23;                                   // fft.rs:348-352
 
+// one Stockham stage of a sub-FFT: everything the inner loop needs, computed on the host so
+// the kernel does no integer division
+struct FftStage {
+    uint16_t r, m, s, tws;   // radix, n/r, stride, twiddle stride (len / n)
+    uint16_t nbf, dp, dq, pad; // butterflies per transform (len / r); (nw / s, nw % s) for nw = 32 warps
+    uint32_t magic;          // ceil(65536 / s): warp / s == (warp * magic) >> 16 for warp < 32, s <= 320
+};
+
 struct FftGeom {
     uint32_t L, real, M, M1, M2, Bn;
     uint32_t ns1, ns2;
-    uint8_t rad1[12], rad2[12];
+    FftStage st1[12], st2[12];
     const float2 *twM;  // exp(-2 pi i j / M), j < M
     const float2 *tw1;  // exp(-2 pi i j / M1)
     const float2 *tw2;  // exp(-2 pi i j / M2)
@@ -47,6 +55,7 @@ struct FftWs {
     uint32_t *locD, *locM, *ovr;  // [FFT_DEC_KCAP]
     float2 *cD, *cM;              // [FFT_DEC_KCAP]
     FftEntry *dlist;              // [FFT_DEC_KCAP] decode-side entry list
+    double *w;                    // [MAX_FRAME + 8] 1 / sample for the MAPE terms of the refinement loop
 };
 
 __device__ inline float2 cmul(float2 a, float2 b) {
@@ -63,19 +72,17 @@ __device__ inline float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x
 // Element e of transform f lives at x[e*FFT_FP + f].  Returns the buffer with the result.
 // ---------------------------------------------------------------------------------------
 template <bool INV>
-__device__ inline float2 *tile_fft(float2 *x, float2 *y, int len, const uint8_t *rad, int ns,
+__device__ inline float2 *tile_fft(float2 *x, float2 *y, int len, const FftStage *stg, int ns,
                                    const float2 *__restrict__ tw, int nb) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    int n = len, s = 1;
+    (void)len;
     for (int st = 0; st < ns; st++) {
-        const int r = rad[st];
-        const int m = n / r;
-        const int nbf = len / r;
-        const int tws = len / n;
+        const FftStage S = stg[st];
+        const int r = S.r, m = S.m, s = S.s, tws = S.tws, nbf = S.nbf;
         if (lane < nb) {
-            // butterfly b = p * s + q; advance (p, q) incrementally instead of dividing per butterfly
-            int p = warp / s, q = warp - p * s;
-            const int dp = nw / s, dq = nw - dp * s;
+            // butterfly b = p * s + q; (p, q) advance incrementally (nw = 32 warps)
+            int p = (warp * (int)S.magic) >> 16, q = warp - p * s;
+            const int dp = S.dp, dq = S.dq;
             for (int b = warp; b < nbf; b += nw, p += dp, q += dq) {
                 if (q >= s) {
                     q -= s;
@@ -120,8 +127,6 @@ __device__ inline float2 *tile_fft(float2 *x, float2 *y, int len, const uint8_t 
         float2 *t = x;
         x = y;
         y = t;
-        n = m;
-        s *= r;
     }
     return x;
 }
@@ -181,6 +186,21 @@ __device__ inline double padded_sample(const double *__restrict__ d, uint32_t N,
     return d[i];
 }
 
+// L2 prefetch of the samples a column tile (columns c0..c0+31, all M1 rows) will read; issued one
+// tile ahead so the DRAM latency overlaps the current tile's butterflies
+__device__ inline void prefetch_col_tile(const double *__restrict__ d, uint32_t N, uint32_t prefix, int M1, int M2,
+                                         int c0, int real) {
+    if (c0 >= M2) return;
+    const int per_row = real ? 4 : 2;  // 128-byte lines per row: 32 columns x (2 or 1) doubles
+    for (int i = threadIdx.x; i < M1 * per_row; i += blockDim.x) {
+        int e = i / per_row, ln = i - e * per_row;
+        uint32_t n = (uint32_t)e * M2 + c0;
+        uint32_t j = (real ? 2 * n : n) + 16 * ln;
+        uint32_t idx = j < prefix ? 0u : j - prefix;
+        if (idx < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(d + idx));
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // forward transform of the padded frame -> Xd[k], keys[k], k < Bn
 // ---------------------------------------------------------------------------------------
@@ -192,6 +212,7 @@ __device__ inline void fft_forward(const double *__restrict__ d, uint32_t N, uin
     // pass 1: column tiles; input built from the samples
     for (int c0 = 0; c0 < M2; c0 += 32) {
         int nb = min(32, M2 - c0);
+        prefetch_col_tile(d, N, prefix, M1, M2, c0 + 32, g.real);
         if (lane < nb) {
             for (int e = warp; e < M1; e += nw) {
                 uint32_t n = (uint32_t)e * M2 + c0 + lane;
@@ -207,7 +228,7 @@ __device__ inline void fft_forward(const double *__restrict__ d, uint32_t N, uin
             }
         }
         __syncthreads();
-        float2 *res = tile_fft<false>(bufA, bufB, M1, g.rad1, g.ns1, g.tw1, nb);
+        float2 *res = tile_fft<false>(bufA, bufB, M1, g.st1, g.ns1, g.tw1, nb);
         tile_twiddle<false>(res, M1, nb, (uint32_t)c0, g.twM, g.twA);
         tile_store_cols(res, ws.W, M1, M2, c0, nb);
     }
@@ -215,7 +236,7 @@ __device__ inline void fft_forward(const double *__restrict__ d, uint32_t N, uin
     for (int r0 = 0; r0 < M1; r0 += 32) {
         int nb = min(32, M1 - r0);
         tile_load_rows(bufA, ws.W, M2, r0, nb);
-        float2 *res = tile_fft<false>(bufA, bufB, M2, g.rad2, g.ns2, g.tw2, nb);
+        float2 *res = tile_fft<false>(bufA, bufB, M2, g.st2, g.ns2, g.tw2, nb);
         tile_store_rows(res, ws.W, M2, r0, nb);
     }
     __threadfence_block();
@@ -269,72 +290,138 @@ __device__ inline uint32_t fft_bin_of(uint32_t i, uint32_t pM, uint32_t pM1, uin
 }
 
 // ---------------------------------------------------------------------------------------
+// radix-select helper: bins are scanned from the largest digit down; returns the digit d with
+//   #(keys with a larger digit) < remaining <= that + hist[d]        (uniform across the CTA)
+// ---------------------------------------------------------------------------------------
+__device__ inline void find_digit(const uint32_t *hist, uint32_t nbins, uint32_t remaining, uint32_t *sh,
+                                  uint32_t *d, uint32_t *above, uint32_t *cnt) {
+    const uint32_t t = threadIdx.x, per = nbins >= blockDim.x ? nbins / blockDim.x : 1;
+    uint32_t loc[4], sum = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+        uint32_t pos = t * per + j;  // position in descending-digit order
+        loc[j] = (j < per && pos < nbins) ? hist[nbins - 1 - pos] : 0u;
+        sum += loc[j];
+    }
+    uint32_t tot;
+    uint32_t excl = block_excl_scan_u32(sum, sh, &tot);
+    if (excl < remaining && remaining <= excl + sum) {
+        uint32_t acc = excl;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+            if (j < per && acc < remaining && remaining <= acc + loc[j]) {
+                sh[102] = nbins - 1 - (t * per + j);
+                sh[103] = acc;
+                sh[106] = loc[j];
+            }
+            acc += loc[j];
+        }
+    }
+    __syncthreads();
+    *d = sh[102];
+    *above = sh[103];
+    *cnt = sh[106];
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
 // top-K of the half spectrum by |z| (fft.rs:231-257), descending, ties by lower bin.
 // Writes list[0..K) and returns K = min(kmax, #nonzero bins).  (pM, pM1, pM2) describe the
-// storage order of ws.keys (pM = 0: natural order).  sm64 must hold next_pow2(K) u64.
+// storage order of ws.keys (pM = 0: natural order).  sm64 must hold FFT_KCAP u64.
+//
+// Two 12-bit histogram passes fix the top 24 bits of the K-th largest key; every key at or
+// above that 24-bit bucket is compacted (a few more than K), sorted, and the first K kept.
+// Only when the boundary bucket is so crowded that the candidates would not fit does a third
+// pass resolve the low 8 bits exactly.
 // ---------------------------------------------------------------------------------------
 __device__ inline uint32_t fft_topk(uint32_t Bn, FftWs ws, uint32_t kmax, FftEntry *list,
                                     unsigned long long *sm64, uint32_t *sh, bool *tie_at_cut,
                                     uint32_t pM, uint32_t pM1, uint32_t pM2) {
     const uint32_t T = blockDim.x, t = threadIdx.x;
-    uint32_t *hist = (uint32_t *)sm64;  // 256 bins (phase-local reuse of the big smem region)
+    uint32_t *hist = (uint32_t *)sm64;  // 4096 bins (phase-local reuse of the big smem region)
     *tie_at_cut = false;
-    // radix select the K-th largest key, 8 bits per level; level 0 also counts zero bins
-    uint32_t prefix = 0, remaining = 0, K = 0, eq_total = 0;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        for (uint32_t i = t; i < 256; i += T) hist[i] = 0;
-        __syncthreads();
-        uint32_t zeros = 0;
-        for (uint32_t b = t; b < Bn; b += T) {
-            uint32_t key = ws.keys[b];
-            zeros += key == 0u;
-            bool in = shift == 24 ? true : (key >> (shift + 8)) == prefix;
-            if (in) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-        }
-        if (shift == 24) {
-            uint32_t nz = Bn - block_sum_u32(zeros, sh);
-            K = min(min(kmax, nz), (uint32_t)FFT_KCAP);
-            if (K == 0) return 0;
-            remaining = K;
-        }
-        __syncthreads();
-        // digit d is selected when  #(keys with a larger digit) < remaining <= that + hist[d]
-        uint32_t hv = t < 256 ? hist[255 - t] : 0u;
-        uint32_t tot;
-        uint32_t above = block_excl_scan_u32(hv, sh, &tot);
-        if (t < 256 && above < remaining && remaining <= above + hv) {
-            sh[102] = 255 - t;
-            sh[103] = above;
-            sh[106] = hv;
-        }
-        __syncthreads();
-        prefix = (prefix << 8) | sh[102];
-        remaining -= sh[103];
-        eq_total = sh[106];
-        __syncthreads();
-    }
-    const uint32_t Tkey = prefix;       // K-th largest key
-    const uint32_t take_eq = remaining;  // how many bins with key == Tkey are taken (lowest index first)
-    const bool tie = eq_total > take_eq;
-    uint32_t P = 1;
-    while (P < K) P <<= 1;
-    unsigned long long *S = sm64;
+    // ---- level 1: top 12 bits (+ count of zero bins)
+    for (uint32_t i = t; i < 4096; i += T) hist[i] = 0;
     __syncthreads();
-    if (!tie) {
-        // every key >= Tkey is taken: unordered compaction (the sort fixes the order)
+    uint32_t zeros = 0;
+    for (uint32_t b0 = t; b0 < Bn; b0 += 4 * T) {
+        uint32_t k[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) k[u] = (b0 + u * T < Bn) ? ws.keys[b0 + u * T] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (k[u] != 0xFFFFFFFFu) {
+                zeros += k[u] == 0u;
+                atomicAdd(&hist[k[u] >> 20], 1u);
+            }
+    }
+    const uint32_t nz = Bn - block_sum_u32(zeros, sh);
+    const uint32_t K = min(min(kmax, nz), (uint32_t)FFT_KCAP);
+    if (K == 0) return 0;
+    uint32_t d1, above1, cnt1;
+    find_digit(hist, 4096, K, sh, &d1, &above1, &cnt1);
+    uint32_t remaining = K - above1;
+    // ---- level 2: next 12 bits inside bucket d1
+    for (uint32_t i = t; i < 4096; i += T) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t b0 = t; b0 < Bn; b0 += 4 * T) {
+        uint32_t k[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) k[u] = (b0 + u * T < Bn) ? ws.keys[b0 + u * T] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (k[u] != 0xFFFFFFFFu && (k[u] >> 20) == d1) atomicAdd(&hist[(k[u] >> 8) & 0xFFFu], 1u);
+    }
+    __syncthreads();
+    uint32_t d2, above2, cnt2;
+    find_digit(hist, 4096, remaining, sh, &d2, &above2, &cnt2);
+    remaining -= above2;  // how many of the cnt2 keys in the boundary bucket belong to the top K
+    const uint32_t T24 = (d1 << 12) | d2;
+    const uint32_t Kover = K - remaining + cnt2;  // candidates if the whole bucket is taken
+    uint32_t Pover = 1;
+    while (Pover < Kover) Pover <<= 1;
+    unsigned long long *S = sm64;
+    uint32_t nsel = K, P;
+    bool tie = false;
+    __syncthreads();
+    if (Pover <= (uint32_t)FFT_KCAP) {
+        // ---- over-select: all keys whose top 24 bits are >= T24 (unordered; the sort orders them)
         if (t == 0) sh[107] = 0;
         __syncthreads();
-        for (uint32_t b = t; b < Bn; b += T) {
-            uint32_t key = ws.keys[b];
-            if (key >= Tkey && key != 0u) {
-                uint32_t pos = atomicAdd(&sh[107], 1u);
-                uint32_t bin = fft_bin_of(b, pM, pM1, pM2);
-                if (pos < P) S[pos] = ((unsigned long long)key << 32) | ((unsigned long long)(0xFFFFFu - bin) << 12) | 0ull;
-            }
+        for (uint32_t b0 = t; b0 < Bn; b0 += 4 * T) {
+            uint32_t k[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) k[u] = (b0 + u * T < Bn) ? ws.keys[b0 + u * T] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (k[u] != 0u && (k[u] >> 8) >= T24) {
+                    uint32_t pos = atomicAdd(&sh[107], 1u);
+                    uint32_t bin = fft_bin_of(b0 + u * T, pM, pM1, pM2);
+                    if (pos < (uint32_t)FFT_KCAP)
+                        S[pos] = ((unsigned long long)k[u] << 32) | ((unsigned long long)(0xFFFFFu - bin) << 12);
+                }
         }
         __syncthreads();
+        nsel = min(sh[107], (uint32_t)FFT_KCAP);
+        P = 1;
+        while (P < nsel) P <<= 1;
     } else {
-        // equal |z| straddle the cut: take the lowest array indices first (ordered compaction)
+        // ---- crowded boundary bucket: resolve the low 8 bits, then take exactly K
+        for (uint32_t i = t; i < 256; i += T) hist[i] = 0;
+        __syncthreads();
+        for (uint32_t b = t; b < Bn; b += T) {
+            uint32_t key = ws.keys[b];
+            if ((key >> 8) == T24) atomicAdd(&hist[key & 255u], 1u);
+        }
+        __syncthreads();
+        uint32_t d3, above3, eq_total;
+        find_digit(hist, 256, remaining, sh, &d3, &above3, &eq_total);
+        const uint32_t take_eq = remaining - above3;
+        const uint32_t Tkey = (T24 << 8) | d3;
+        tie = eq_total > take_eq;
+        P = 1;
+        while (P < K) P <<= 1;
+        // equal |z| may straddle the cut: take the lowest array indices first (ordered compaction)
         uint32_t base = 0, eqbase = 0;
         for (uint32_t b0 = 0; b0 < Bn; b0 += T) {
             uint32_t b = b0 + t;
@@ -355,8 +442,9 @@ __device__ inline uint32_t fft_topk(uint32_t Bn, FftWs ws, uint32_t kmax, FftEnt
             eqbase += eqtot;
             __syncthreads();
         }
+        nsel = K;
     }
-    for (uint32_t i = K + t; i < P; i += T) S[i] = 0ull;
+    for (uint32_t i = nsel + t; i < P; i += T) S[i] = 0ull;
     __syncthreads();
     // bitonic sort, descending: (|z| desc, bin asc)
     for (uint32_t k2 = 2; k2 <= P; k2 <<= 1) {
@@ -375,6 +463,8 @@ __device__ inline uint32_t fft_topk(uint32_t Bn, FftWs ws, uint32_t kmax, FftEnt
             __syncthreads();
         }
     }
+    // equal |z| on both sides of the K cut?
+    if (nsel > K && (uint32_t)(S[K - 1] >> 32) == (uint32_t)(S[K] >> 32)) tie = true;
     for (uint32_t r = t; r < K; r += T) {
         uint32_t bin = 0xFFFFFu - (uint32_t)((S[r] >> 12) & 0xFFFFFull);
         // array index of this bin (inverse of fft_bin_of)
@@ -467,8 +557,10 @@ __device__ inline void fft_prepare_entries(const FftGeom &g, FftWs ws, const Fft
 // inverse transform of the first `c` list entries; Epi(j, value) is called once for every
 // time index j < L with the unnormalised real output (all threads participate).
 // ---------------------------------------------------------------------------------------
+// (pf_d, pf_N, pf_prefix): samples the epilogue will read, prefetched one tile ahead (nullptr: none)
 template <class Epi>
-__device__ inline void fft_inverse(const FftGeom &g, FftWs ws, uint32_t c, float2 *sm, Epi epi) {
+__device__ inline void fft_inverse(const FftGeom &g, FftWs ws, uint32_t c, float2 *sm, Epi epi,
+                                   const double *pf_d = nullptr, uint32_t pf_N = 0, uint32_t pf_prefix = 0) {
     float2 *bufA = sm, *bufB = sm + FFT_TILE_F2;
     const int M1 = g.M1, M2 = g.M2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -501,17 +593,19 @@ __device__ inline void fft_inverse(const FftGeom &g, FftWs ws, uint32_t c, float
             }
         }
         __syncthreads();
-        float2 *res = tile_fft<true>(bufA, bufB, M2, g.rad2, g.ns2, g.tw2, nb);
+        float2 *res = tile_fft<true>(bufA, bufB, M2, g.st2, g.ns2, g.tw2, nb);
         tile_twiddle<true>(res, M2, nb, (uint32_t)r0, g.twM, g.twB);
         tile_store_rows(res, ws.W, M2, r0, nb);
     }
     __threadfence_block();
     __syncthreads();
     // pass 2: column tiles + epilogue
+    if (pf_d) prefetch_col_tile(pf_d, pf_N, pf_prefix, M1, M2, 0, g.real);
     for (int c0 = 0; c0 < M2; c0 += 32) {
         int nb = min(32, M2 - c0);
+        if (pf_d) prefetch_col_tile(pf_d, pf_N, pf_prefix, M1, M2, c0 + 32, g.real);
         tile_load_cols(bufA, ws.W, M1, M2, c0, nb);
-        float2 *res = tile_fft<true>(bufA, bufB, M1, g.rad1, g.ns1, g.tw1, nb);
+        float2 *res = tile_fft<true>(bufA, bufB, M1, g.st1, g.ns1, g.tw1, nb);
         if (lane < nb) {
             for (int e = warp; e < M1; e += nw) {
                 uint32_t n = (uint32_t)e * M2 + c0 + lane;
@@ -531,6 +625,17 @@ __device__ inline void fft_inverse(const FftGeom &g, FftWs ws, uint32_t c, float
 // FFT::round (fft.rs:208-218) of `re / len_f32`
 __device__ inline double fft_round(float x, float vminf, float vmaxf) {
     double out = round5_exact((double)x);
+    if (out > (double)vmaxf) return (double)vmaxf;
+    if (out < (double)vminf) return (double)vminf;
+    return out;
+}
+
+// same, for the refinement loop only: `* 1e-5` instead of the true `/ 1e5` (<= 1 ulp off; the error
+// it feeds is compared against thresholds)
+__device__ inline double fft_round_fast(float x, double o, float vminf, float vmaxf) {
+    double n = round(__dmul_rn((double)x, 100000.0));
+    double out = n * 1e-5;
+    if (fabs(out - o) <= fabs(o) * 4.5e-16) out = __ddiv_rn(n, 100000.0);  // exact zero terms stay exact
     if (out > (double)vmaxf) return (double)vmaxf;
     if (out < (double)vminf) return (double)vminf;
     return out;

@@ -32,6 +32,7 @@ __device__ inline FftWs fft_slot(const SlotPool &p, int s) {
     w.cD = p.fft_cD + (size_t)s * FFT_DEC_KCAP;
     w.cM = p.fft_cM + (size_t)s * FFT_DEC_KCAP;
     w.dlist = p.fft_dlist + (size_t)s * FFT_DEC_KCAP;
+    w.w = p.fft_w + (size_t)s * (MAX_FRAME + 8);
     return w;
 }
 
@@ -93,15 +94,20 @@ __global__ void k_plan(FrameWork *fr, uint32_t n) {
 // polynomial / idw
 // =========================================================================================
 __global__ void __launch_bounds__(BLOCK) k_poly(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
-                                                double max_err, const double *__restrict__ inv_d2, unsigned *q) {
+                                                double max_err, const double *__restrict__ inv_d2, SlotPool pool,
+                                                unsigned *q) {
     __shared__ double shd[64];
+    __shared__ PolyTab tab;
     __shared__ int s_item;
+    PolyWs ws;
+    ws.slope = pool.poly_slope + (size_t)blockIdx.x * (MAX_FRAME + 8);
+    ws.w = pool.poly_w + (size_t)blockIdx.x * (MAX_FRAME + 8);
     for (;;) {
         int i = queue_next(q, &s_item);
         if (i >= (int)n) break;
         FrameWork *fw = &fr[i];
         if (!fw->need_poly) continue;
-        poly_frame(samples + fw->off, fw, max_err, inv_d2, shd);
+        poly_frame(samples + fw->off, fw, max_err, inv_d2, shd, ws, &tab);
     }
 }
 
@@ -259,15 +265,27 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
 
     const float Lf = (float)L;
     const double Ld = (double)L;
+    bool have_w = false;
     auto evaluate = [&](uint32_t c) -> double {
         double acc = 0.0;
         auto epi = [&](uint32_t j, float v) {
-            double out = fft_round(__fdiv_rn(v, Lf), vminf, vmaxf);
-            double o = padded_sample(d, N, prefix, j);
-            acc += fabs(__ddiv_rn(__dsub_rn(out, o), o));
+            uint32_t ix = j < prefix ? 0u : j - prefix;  // gibbs padding replicates the edge samples
+            if (ix >= N) ix = N - 1;
+            const double o = d[ix];
+            double out = fft_round_fast(__fdiv_rn(v, Lf), o, vminf, vmaxf);
+            // reciprocal for the MAPE term (utils/error.rs:110-113): computed by the first
+            // evaluation, reused by the (up to 22) later ones
+            double w;
+            if (have_w) {
+                w = ws.w[ix];
+            } else {
+                w = __ddiv_rn(1.0, o);
+                ws.w[ix] = w;
+            }
+            acc += mape_term(out, o, w);
         };
         if (gi >= 0) {
-            fft_inverse(*sg, ws, c, sm, epi);
+            fft_inverse(*sg, ws, c, sm, epi, d, N, prefix);
         } else {
             for (uint32_t j = t; j < N; j += T) {
                 float v = 0.f;
@@ -286,6 +304,7 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
             }
         }
         double s = block_sum(acc, shd);
+        have_w = true;
         return __ddiv_rn(s, Ld);
     };
 
@@ -979,8 +998,8 @@ void launch_stats(FrameWork *fr, uint32_t n, const double *samples, unsigned *q,
 }
 void launch_plan(FrameWork *fr, uint32_t n, cudaStream_t st) { k_plan<<<(n + 255) / 256, 256, 0, st>>>(fr, n); }
 void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_err, const double *inv_d2,
-                 unsigned *q, cudaStream_t st) {
-    k_poly<<<grid_for(n, 2 * sms()), BLOCK, 0, st>>>(fr, n, samples, max_err, inv_d2, q);
+                 SlotPool pool, unsigned *q, cudaStream_t st) {
+    k_poly<<<grid_for(n, pool.poly_slots), BLOCK, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);
 }
 void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err, SlotPool pool, unsigned *q,
                 cudaStream_t st) {

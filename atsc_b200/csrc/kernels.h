@@ -19,7 +19,11 @@ struct SlotPool {
     float2 *fft_W, *fft_Xd, *fft_cD, *fft_cM;
     uint32_t *fft_keys, *fft_rank, *fft_locD, *fft_locM, *fft_ovr;
     FftEntry *fft_dlist;
+    double *fft_w;
     int fft_slots;
+    // polynomial refinement loop (poly.cuh)
+    double *poly_slope, *poly_w;  // [MAX_FRAME + 8] per slot
+    int poly_slots;
     // decode scratch
     double *dec_pts;     // [MAX_FRAME + 8] per slot: decoded polynomial points / RLE values
     uint32_t *dec_mark;  // [MAX_FRAME + 8] per slot: RLE run-start markers
@@ -41,7 +45,7 @@ struct DecFrame {
 void launch_stats(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st);
 void launch_plan(FrameWork *fr, uint32_t n, cudaStream_t st);
 void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_err, const double *inv_d2,
-                 unsigned *q, cudaStream_t st);
+                 SlotPool pool, unsigned *q, cudaStream_t st);
 void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err, SlotPool pool,
                 unsigned *q, cudaStream_t st);
 void launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,

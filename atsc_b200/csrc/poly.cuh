@@ -88,20 +88,127 @@ __device__ inline double idw_eval_at(const PolyKeys &k, uint32_t x, PtsFn pts,
     return acc;
 }
 
+// per-CTA-slot scratch of the refinement loop
+struct PolyWs {
+    double *slope;  // [MAX_FRAME + 8] central-difference slope at every key of the current step
+    double *w;      // [MAX_FRAME]     1 / sample, computed once per frame
+};
+constexpr int POLY_TAB = 136;  // step <= 133 (polynomial.rs:290 with >= max(3, N/100) points)
+struct PolyTab {
+    double lin0[POLY_TAB];  // 1 - t
+    double tt[POLY_TAB];    // t = j / step
+    double h00[POLY_TAB], h10[POLY_TAB], h01[POLY_TAB], h11[POLY_TAB];  // cubic Hermite basis at t
+};
+
+// One MAPE term |(out - o) / o| (utils/error.rs:110-113) through the precomputed reciprocal
+// w = 1/o: deviates from the true division by <= 1 ulp (absorbed by the near-tie tolerance, the
+// error only feeds threshold tests) while exact zeros stay exactly zero.  A zero sample keeps the
+// reference's semantics: w = inf gives |out * inf - 1| = inf (out != 0) or NaN (out == 0), SURVEY H5.
+__device__ inline double mape_term(double out, double o, double w) {
+    return (out == o && o != 0.0) ? 0.0 : fabs(fma(out, w, -1.0));
+}
+// (x * 1e5).round() / 1e5 for the error loops.  `* 1e-5` replaces the true division (<= 1 ulp off)
+// unless the result lands within 2 ulp of the original sample `o`: an exactly reproduced sample
+// must give an exactly zero error term (lossless `-e 0` relies on `error <= 0`), so that case
+// takes the IEEE quotient.  Only the decompressor always needs the exact quotient.
+__device__ inline double round5_loop(double x, double o) {
+    double n = round(__dmul_rn(x, 100000.0));
+    double out = n * 1e-5;
+    if (fabs(out - o) <= fabs(o) * 4.5e-16) out = __ddiv_rn(n, 100000.0);
+    return out;
+}
+__device__ inline double round_and_limit5_fast(double x, double o, double mn, double mx) {
+    double out = round5_loop(x, o);
+    if (out < mn) return mn;
+    if (out > mx) return mx;
+    return out;
+}
+
 // MAPE (utils/error.rs:104-116) of one candidate step against the frame; block-wide.
+// Catmull-Rom path: identical value arithmetic to poly_eval_at (same operations, same order),
+// but everything that depends only on the offset inside a segment comes from a table and the
+// per-key tangents from a pre-pass, so the inner loop has no division.
 __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys &k, int ptype,
                                    double vmin, double vmax, const double *__restrict__ inv_d2,
-                                   double *scratch) {
+                                   PolyWs ws, PolyTab *tab, bool have_w, double *scratch) {
+    const uint32_t N = k.N, step = k.step, K = k.K, T = blockDim.x, t = threadIdx.x;
     double acc = 0.0;
     auto pts = [&](uint32_t j) { return d[poly_pos(k, j)]; };
-    for (uint32_t x = threadIdx.x; x < k.N; x += blockDim.x) {
-        double v = ptype ? idw_eval_at(k, x, pts, inv_d2) : poly_eval_at(k, x, pts);
-        double out = round_and_limit5(v, vmin, vmax);
+    if (ptype || step >= (uint32_t)POLY_TAB || K < 2) {
+        for (uint32_t x = t; x < N; x += T) {
+            double v = ptype ? idw_eval_at(k, x, pts, inv_d2) : poly_eval_at(k, x, pts);
+            double o = d[x];
+            double out = round_and_limit5_fast(v, o, vmin, vmax);
+            double w = have_w ? ws.w[x] : __ddiv_rn(1.0, o);
+            if (!have_w) ws.w[x] = w;
+            acc += mape_term(out, o, w);
+        }
+        double s = block_sum(acc, scratch);
+        return __ddiv_rn(s, (double)N);
+    }
+    // ---- tables over the offset j inside a regular segment
+    const double stepd = (double)step;
+    for (uint32_t j = t; j < step; j += T) {
+        double tt = __ddiv_rn((double)j, stepd);
+        double two_t = __dmul_rn(tt, 2.0), three_t = __dmul_rn(tt, 3.0);
+        double t2 = __dmul_rn(tt, tt), t3 = __dmul_rn(t2, tt);
+        double two_t3 = __dmul_rn(t2, two_t), two_t2 = __dmul_rn(tt, two_t), three_t2 = __dmul_rn(tt, three_t);
+        tab->tt[j] = tt;
+        tab->lin0[j] = __dsub_rn(1.0, tt);
+        tab->h00[j] = __dadd_rn(__dsub_rn(two_t3, three_t2), 1.0);
+        tab->h10[j] = __dadd_rn(__dsub_rn(t3, two_t2), tt);
+        tab->h01[j] = __dsub_rn(three_t2, two_t3);
+        tab->h11[j] = __dsub_rn(t3, t2);
+    }
+    // ---- central-difference slope at every interior key: (v[j+1] - v[j-1]) / (pos[j+1] - pos[j-1])
+    for (uint32_t j = 1 + t; j + 1 < K; j += T) {
+        uint32_t pa = poly_pos(k, j - 1), pb = poly_pos(k, j + 1);
+        ws.slope[j] = __ddiv_rn(__dsub_rn(d[pb], d[pa]), __dsub_rn((double)pb, (double)pa));
+    }
+    __syncthreads();
+    const uint32_t Kreg = k.Kreg;
+    const uint32_t last_reg = (Kreg - 1) * step;  // position of the last regular key
+    // (i, j) = (x / step, x % step) advanced incrementally
+    uint32_t i = t / step, j = t - i * step;
+    const uint32_t di = T / step, dj = T - di * step;
+    for (uint32_t x = t; x < N; x += T, i += di, j += dj) {
+        if (j >= step) {
+            j -= step;
+            i++;
+        }
+        double v;
+        if (x == N - 1) {
+            v = d[N - 1];
+        } else if (i == Kreg - 1) {
+            // irregular last segment [last_reg, N-1]: always Linear (it is segment K-2)
+            double at = (double)last_reg, bt = (double)(N - 1);
+            double nt = __ddiv_rn(__dsub_rn((double)x, at), __dsub_rn(bt, at));
+            v = __dadd_rn(__dmul_rn(d[last_reg], __dsub_rn(1.0, nt)), __dmul_rn(d[N - 1], nt));
+        } else {
+            const double av = d[i * step];
+            const uint32_t pb = (i + 1 < Kreg) ? (i + 1) * step : N - 1;  // == (i+1)*step here
+            const double bv = d[pb];
+            const bool catmull = (i > 0) && (K - i > 2);
+            if (!catmull) {
+                v = __dadd_rn(__dmul_rn(av, tab->lin0[j]), __dmul_rn(bv, tab->tt[j]));
+            } else {
+                double m0 = __dmul_rn(ws.slope[i], stepd);
+                double m1 = __dmul_rn(ws.slope[i + 1], stepd);
+                double c0 = __dmul_rn(av, tab->h00[j]);
+                double c1 = __dmul_rn(m0, tab->h10[j]);
+                double c2 = __dmul_rn(bv, tab->h01[j]);
+                double c3 = __dmul_rn(m1, tab->h11[j]);
+                v = __dadd_rn(__dadd_rn(__dadd_rn(c0, c1), c2), c3);
+            }
+        }
         double o = d[x];
-        acc += fabs(__ddiv_rn(__dsub_rn(out, o), o));
+        double out = round_and_limit5_fast(v, o, vmin, vmax);
+        double w = have_w ? ws.w[x] : __ddiv_rn(1.0, o);
+        if (!have_w) ws.w[x] = w;
+        acc += mape_term(out, o, w);
     }
     double s = block_sum(acc, scratch);
-    return __ddiv_rn(s, (double)k.N);
+    return __ddiv_rn(s, (double)N);
 }
 
 // payload size of a Polynomial struct (polynomial.rs:54-87) with K points at `step`
@@ -133,7 +240,7 @@ __device__ inline bool poly_loop_near_tie(double cur, double target) {
 // Runs the reference's refinement loop for one frame. All threads of the CTA call.
 // Writes poly_* fields of fw (thread 0).  `sh` = shared scratch (>= 40 doubles).
 __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, double max_err,
-                                  const double *__restrict__ inv_d2, double *sh) {
+                                  const double *__restrict__ inv_d2, double *sh, PolyWs ws, PolyTab *tab) {
     const uint32_t N = fw->len;
     const double vmin = fw->vmin, vmax = fw->vmax;
     const int ptype = fw->poly_type;
@@ -155,6 +262,7 @@ __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, d
             const double target = round_f64_dec(max_err, 3);
             uint32_t prev_step = 0;
             double prev_err = 0.0;
+            bool have_w = false;
             while (target < round_f64_dec(cur, 4)) {
                 it++;
                 uint32_t points = baseline + jump;
@@ -166,7 +274,8 @@ __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, d
                 } else if (step == 1 && it <= 22) {
                     cur = 0.0;  // value unused: the `len == data_len` exit below overrides it
                 } else {
-                    cur = poly_mape(d, k, ptype, vmin, vmax, inv_d2, sh);
+                    cur = poly_mape(d, k, ptype, vmin, vmax, inv_d2, ws, tab, have_w, sh);
+                    have_w = true;
                 }
                 prev_step = step;
                 prev_err = cur;

@@ -42,26 +42,47 @@ __device__ inline void frame_stats(const double *__restrict__ d, uint32_t N, Fra
                                    StatsSmem *sm) {
     MinMaxIdx mn = {0.0, 0xFFFFFFFFu}, mx = {0.0, 0xFFFFFFFFu};
     uint32_t frac = 0, runs = 0, idxb = 0;
-    for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
-        double v = d[i];
-        bool f;
-        (void)split_n(v, &f);
-        frac |= f ? 1u : 0u;
-        if (v == v) {  // NaN never wins a strict comparison (optimizer/utils.rs:57-64)
-            if (mn.i == 0xFFFFFFFFu || v < mn.v) {
-                mn.v = v;
-                mn.i = i;
-            }
-            if (mx.i == 0xFFFFFFFFu || v > mx.v) {
-                mx.v = v;
-                mx.i = i;
-            }
+    // 4 independent coalesced loads in flight per thread; the right-hand neighbour comes from a
+    // warp shuffle (only lane 31 touches memory again)
+    const uint32_t T = blockDim.x;
+    const int ln = threadIdx.x & 31;
+    for (uint32_t i0 = 0; i0 < N; i0 += 4 * T) {
+        double v[4], nx[4];
+        uint32_t ix[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            ix[u] = i0 + u * T + threadIdx.x;
+            v[u] = ix[u] < N ? d[ix[u]] : 0.0;
         }
-        // rle.rs:154: run ends where the next value differs (or at the end)
-        bool end = (i + 1 >= N) || (d[i + 1] != v);
-        if (end) {
-            runs++;
-            if (i + 1 < N) idxb += varint_len((uint64_t)i + 1);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            nx[u] = __shfl_down_sync(0xffffffffu, v[u], 1);
+            if (ln == 31 && ix[u] + 1 < N) nx[u] = d[ix[u] + 1];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (ix[u] >= N) continue;
+            const uint32_t i = ix[u];
+            const double val = v[u];
+            bool f;
+            (void)split_n(val, &f);
+            frac |= f ? 1u : 0u;
+            if (val == val) {  // NaN never wins a strict comparison (optimizer/utils.rs:57-64)
+                if (mn.i == 0xFFFFFFFFu || val < mn.v) {
+                    mn.v = val;
+                    mn.i = i;
+                }
+                if (mx.i == 0xFFFFFFFFu || val > mx.v) {
+                    mx.v = val;
+                    mx.i = i;
+                }
+            }
+            // rle.rs:154: run ends where the next value differs (or at the end)
+            bool end = (i + 1 >= N) || (nx[u] != val);
+            if (end) {
+                runs++;
+                if (i + 1 < N) idxb += varint_len((uint64_t)i + 1);
+            }
         }
     }
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
