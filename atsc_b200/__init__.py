@@ -27,6 +27,7 @@ API_SYMBOLS = [
     "atsc_gpu_create", "atsc_gpu_destroy", "atsc_gpu_last_error", "atsc_gpu_host_alloc", "atsc_gpu_host_free",
     "atsc_gpu_compress_frames", "atsc_gpu_decompress_frames", "atsc_plan_chunk_sizes",
     "atsc_gpu_compress_series", "atsc_gpu_decompress_series", "atsc_gpu_launch_count", "atsc_gpu_kernel_ms",
+    "atsc_plan_shards", "atsc_wbro_decode", "atsc_wbro_encode", "atsc_csv_read_values",
 ]
 KERNEL_NAMES = ["stats", "poly", "rle", "fft", "select", "emit", "decode", "reserved"]
 
@@ -79,6 +80,14 @@ def load_library(build_if_missing=True):
     L.atsc_gpu_host_free.argtypes = [vp]
     L.atsc_gpu_launch_count.restype = C.c_uint64
     L.atsc_gpu_launch_count.argtypes = [vp]
+    L.atsc_plan_shards.restype = None
+    L.atsc_plan_shards.argtypes = [u32p, C.c_uint32, C.c_uint32, u32p]
+    L.atsc_wbro_decode.restype = C.c_int64
+    L.atsc_wbro_decode.argtypes = [vp, C.c_uint64, vp, C.c_uint64]
+    L.atsc_wbro_encode.restype = C.c_uint64
+    L.atsc_wbro_encode.argtypes = [vp, C.c_uint64, vp, C.c_uint64]
+    L.atsc_csv_read_values.restype = C.c_int64
+    L.atsc_csv_read_values.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_char_p, C.c_char_p, vp, C.c_uint64]
     L.atsc_gpu_kernel_ms.restype = None
     L.atsc_gpu_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
     L.atsc_gpu_compress_frames.restype = C.c_int
@@ -108,6 +117,55 @@ def chunk_sizes(n):
 
 def _ptr(a):
     return C.c_void_p(a.ctypes.data)
+
+
+def plan_shards(frame_len, n_parts):
+    """atsc_plan_shards: contiguous frame ranges balanced by sample count (host-only)."""
+    L = load_library()
+    fl = np.ascontiguousarray(frame_len, dtype=np.uint32)
+    first = np.zeros(n_parts + 1, dtype=np.uint32)
+    L.atsc_plan_shards(fl.ctypes.data_as(C.POINTER(C.c_uint32)), len(fl), n_parts,
+                       first.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return [int(x) for x in first]
+
+
+def wbro_decode(blob):
+    """WavBrro::from_file on a file image (wavbrro/src/wavbrro.rs:103); host-only."""
+    L = load_library()
+    b = np.frombuffer(bytes(blob), dtype=np.uint8)
+    n = L.atsc_wbro_decode(_ptr(b), len(b), None, 0)
+    if n < 0:
+        raise AtscError(5, f"not a WBRO file ({n})")
+    out = np.empty(max(n, 1), dtype=np.float64)
+    L.atsc_wbro_decode(_ptr(b), len(b), _ptr(out), n)
+    return out[:n]
+
+
+def wbro_encode(samples):
+    """WavBrro::to_file_with_data (wavbrro/src/wavbrro.rs:114); host-only."""
+    L = load_library()
+    a = np.ascontiguousarray(samples, dtype=np.float64)
+    if len(a) == 0:
+        a = np.zeros(1)
+        n = 0
+    else:
+        n = len(a)
+    size = L.atsc_wbro_encode(_ptr(a), n, None, 0)
+    out = np.empty(size, dtype=np.uint8)
+    L.atsc_wbro_encode(_ptr(a), n, _ptr(out), size)
+    return out.tobytes()
+
+
+def csv_read_values(text, has_header=True, time_field="time", value_field="value"):
+    """atsc/src/csv.rs:36-98; host-only."""
+    L = load_library()
+    t = text.encode() if isinstance(text, str) else bytes(text)
+    n = L.atsc_csv_read_values(t, len(t), 1 if has_header else 0, time_field.encode(), value_field.encode(), None, 0)
+    if n < 0:
+        raise AtscError(5, f"csv error {n}")
+    out = np.empty(max(n, 1), dtype=np.float64)
+    L.atsc_csv_read_values(t, len(t), 1 if has_header else 0, time_field.encode(), value_field.encode(), _ptr(out), n)
+    return out[:n]
 
 
 class Context:

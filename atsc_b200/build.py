@@ -13,7 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libatsc_gpu.so")
-SOURCES = ["kernels.cu", "api.cu", "stream.cpp"]
+CLI = os.path.join(HERE, "atsc")
+SOURCES = ["kernels.cu", "api.cu", "stream.cpp", "ingest.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "-Xcompiler", "-fPIC",
@@ -24,12 +25,13 @@ NVCC_FLAGS = [
 
 def _deps():
     files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    files.append(os.path.join(HERE, "host", "atsc_cli.cpp"))
     files.append(os.path.join(os.path.dirname(HERE), "include", "atsc_gpu.h"))
     return files
 
 
 def is_stale():
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(CLI):
         return True
     t = os.path.getmtime(OUT)
     return any(os.path.getmtime(f) > t for f in _deps())
@@ -56,6 +58,10 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed on {s}")
     cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.check_call(cmd)
+    # the `atsc` command line (reference option surface) on top of the library
+    cli_src = os.path.join(HERE, "host", "atsc_cli.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", cli_src, "-o", CLI, "-L" + HERE, "-latsc_gpu",
+                           "-Wl,-rpath,$ORIGIN"])
     return OUT
 
 

@@ -657,18 +657,13 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
     return ATSC_OK;
 }
 
-// contiguous ranges of frames balanced by sample count
+// contiguous ranges of frames balanced by sample count (atsc_plan_shards, ingest.cpp)
 std::vector<std::vector<uint32_t>> shard(const uint32_t *lens, uint32_t n, size_t ndev) {
     std::vector<std::vector<uint32_t>> parts(ndev);
-    uint64_t total = 0;
-    for (uint32_t i = 0; i < n; i++) total += lens[i];
-    uint64_t acc = 0;
-    size_t d = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        while (d + 1 < ndev && acc >= (total * (d + 1)) / ndev) d++;
-        parts[d].push_back(i);
-        acc += lens[i];
-    }
+    std::vector<uint32_t> first(ndev + 1);
+    atsc_plan_shards(lens, n, (uint32_t)ndev, first.data());
+    for (size_t d = 0; d < ndev; d++)
+        for (uint32_t i = first[d]; i < first[d + 1]; i++) parts[d].push_back(i);
     return parts;
 }
 

@@ -147,6 +147,24 @@ int atsc_gpu_decompress_series(atsc_ctx *ctx, const uint8_t *bro_buf, const uint
                                const uint64_t *bro_len, uint32_t n_series, double *out_samples,
                                const uint64_t *out_off, uint64_t *out_count);
 
+/* ---- host-only helpers either side of the path (no GPU needed) ------------------- */
+
+/* contiguous frame ranges balanced by sample count: how a multi-device context (and bench.py's
+ * ranks) shard a call.  out_first has n_parts + 1 entries; part p = frames [first[p], first[p+1]). */
+void atsc_plan_shards(const uint32_t *frame_len, uint32_t n_frames, uint32_t n_parts, uint32_t *out_first);
+
+/* WBRO container (wavbrro/src/wavbrro.rs:103-132): whole-file image <-> samples.
+ * decode returns the sample count (copies min(count, cap)), -1 bad header, -2 corrupt archive;
+ * encode returns the file size and writes it when it fits in cap. */
+int64_t atsc_wbro_decode(const uint8_t *file, uint64_t len, double *out, uint64_t cap);
+uint64_t atsc_wbro_encode(const double *samples, uint64_t n, uint8_t *out, uint64_t cap);
+
+/* CSV value column (atsc/src/csv.rs:36-98).  has_header: locate time_field / value_field by name
+ * (the time column is located but never parsed, like the reference); else first column.
+ * Returns the value count, -1 time field missing, -2 value field missing, -3 parse failure. */
+int64_t atsc_csv_read_values(const char *text, uint64_t len, int has_header, const char *time_field,
+                             const char *value_field, double *out, uint64_t cap);
+
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t atsc_gpu_launch_count(const atsc_ctx *ctx);
 
