@@ -209,16 +209,19 @@ class Context:
 
     # ------------------------------------------------------------------ frame level (C ABI)
     def compress_frames(self, samples, frame_off, frame_len, compressor=AUTO, max_error=0.05, speed=0,
-                        bounded=True, payload_cap=None, samples_ptr=None):
+                        bounded=True, payload_cap=None, samples_ptr=None, payload_out=None):
         """atsc_gpu_compress_frames.  `samples` is a float64 numpy array (host) or, with
         samples_ptr, a raw device pointer.  Returns (FrameOut array, payload bytes ndarray)."""
         fo = np.ascontiguousarray(frame_off, dtype=np.uint64)
         fl = np.ascontiguousarray(frame_len, dtype=np.uint32)
         n = len(fl)
         out = (FrameOut * max(n, 1))()
-        if payload_cap is None:
-            payload_cap = int(fl.astype(np.uint64).sum()) * 16 + 64 * n + 64
-        payload = np.empty(payload_cap, dtype=np.uint8)
+        if payload_out is not None:
+            payload, payload_cap = payload_out, len(payload_out)  # caller-owned (e.g. page-locked) buffer
+        else:
+            if payload_cap is None:
+                payload_cap = int(fl.astype(np.uint64).sum()) * 16 + 64 * n + 64
+            payload = np.empty(payload_cap, dtype=np.uint8)
         used = C.c_uint64()
         if samples_ptr is None:
             samples = np.ascontiguousarray(samples, dtype=np.float64)

@@ -105,8 +105,17 @@ int grow(Device &D, T *&p, size_t &cap, size_t need, bool pinned_host = false) {
 
 // ---------------------------------------------------------------- FFT geometry tables
 void radices_of(uint32_t len, FftStage *stg, uint32_t *ns) {
+    // radices {9, 8, 4, 3, 2}: as few Stockham stages (shared-memory round trips) as possible
     uint8_t rad[16];
     uint32_t k = 0, n = len;
+    while (n % 9 == 0) {
+        rad[k++] = 9;
+        n /= 9;
+    }
+    while (n % 8 == 0) {
+        rad[k++] = 8;
+        n /= 8;
+    }
     while (n % 4 == 0) {
         rad[k++] = 4;
         n /= 4;
@@ -254,8 +263,8 @@ int device_init(Device &D) {
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, D.id));
     SlotPool &P = D.pool;
     P.rle_slots = 2 * sms;
-    P.fft_slots = sms;
-    P.dec_slots = sms;
+    P.fft_slots = 2 * sms;  // k_fft / k_decode run two 512-thread CTAs per SM
+    P.dec_slots = 2 * sms;
     size_t rs = (size_t)P.rle_slots;
     CK(cudaMalloc((void **)&P.rle_k0, rs * MAX_FRAME * 8));
     CK(cudaMalloc((void **)&P.rle_k1, rs * MAX_FRAME * 8));
@@ -328,8 +337,11 @@ struct FrameReq {
 
 // runs the pipeline for reqs[0..n) whose samples live at d_samples (device); results are left
 // in D.h_frames[0..n); payload bytes (if any) in D.h_payload[0..*payload_total)
+// direct_dst != nullptr: page-locked destination (capacity direct_cap) the payload is copied to
+// straight from the device; *direct is set when that happened (else the bytes are in D.h_payload)
 int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &reqs, float max_error_f32,
-             uint64_t *payload_total) {
+             uint64_t *payload_total, uint8_t *direct_dst = nullptr, uint64_t direct_cap = 0, bool *direct = nullptr) {
+    if (direct) *direct = false;
     const uint32_t n = (uint32_t)reqs.size();
     const double max_err = (double)max_error_f32;  // `max_error as f64` (frame/mod.rs:67,87)
     int rc;
@@ -403,13 +415,15 @@ int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &re
     uint64_t total = *D.h_total;
     *payload_total = total;
     if (total) {
+        const bool to_user = direct_dst && total <= direct_cap;
         if ((rc = grow(D, D.d_payload, D.payload_cap, (size_t)total + 16))) return rc;
-        if ((rc = grow(D, D.h_payload, D.h_payload_cap, (size_t)total + 16, true))) return rc;
+        if (!to_user && (rc = grow(D, D.h_payload, D.h_payload_cap, (size_t)total + 16, true))) return rc;
         CK(cudaEventRecord(D.ev[6], D.st));
         launch_emit(D.d_frames, n, d_samples, D.geoms_dev, D.pool, D.d_arena, D.d_payload, D.queues + 5, D.st);
         CK(cudaEventRecord(D.ev[7], D.st));
         D.launches++;
-        CK(cudaMemcpyAsync(D.h_payload, D.d_payload, (size_t)total, cudaMemcpyDeviceToHost, D.st));
+        CK(cudaMemcpyAsync(to_user ? direct_dst : D.h_payload, D.d_payload, (size_t)total, cudaMemcpyDeviceToHost, D.st));
+        if (direct) *direct = to_user;
     }
     CK(cudaMemcpyAsync(D.h_frames, D.d_frames, (size_t)n * sizeof(FrameWork), cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
@@ -442,7 +456,17 @@ struct PayloadSink {
     uint8_t *buf;
     uint64_t cap, used;
     bool overflow;
+    bool pinned;  // buf is page-locked host memory: payloads are copied to it straight from the device
 };
+
+bool is_pinned_host(const void *p) {
+    cudaPointerAttributes a;
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
 
 static const uint32_t COMPRESSION_SPEED[7] = {2147483647u, 4096, 2048, 1024, 512, 256, 128};  // frame/mod.rs:22
 
@@ -534,7 +558,9 @@ int compress_on_device(Device &D, const double *samples, bool dev_ptr, const uin
             }
         }
         uint64_t ptotal;
-        int rc = run_wave(D, d_samples, reqs, max_error, &ptotal);
+        bool direct = false;
+        int rc = run_wave(D, d_samples, reqs, max_error, &ptotal, sink.pinned ? sink.buf + sink.used : nullptr,
+                          sink.pinned && sink.cap > sink.used ? sink.cap - sink.used : 0, &direct);
         if (rc) return rc;
         for (uint32_t k = 0; k < n; k++) {
             const FrameWork &f = D.h_frames[k];
@@ -550,7 +576,7 @@ int compress_on_device(Device &D, const double *samples, bool dev_ptr, const uin
         }
         if (sink.used + ptotal > sink.cap)
             sink.overflow = true;
-        else if (ptotal)
+        else if (ptotal && !direct)
             memcpy(sink.buf + sink.used, D.h_payload, ptotal);
         sink.used += ptotal;
         pos = end;
@@ -770,7 +796,7 @@ int atsc_gpu_compress_frames(atsc_ctx *ctx, const double *samples, const uint64_
     if (nd == 1) {
         std::vector<uint32_t> idx(n_frames);
         for (uint32_t i = 0; i < n_frames; i++) idx[i] = i;
-        PayloadSink sink{payload_buf, payload_cap, 0, false};
+        PayloadSink sink{payload_buf, payload_cap, 0, false, is_pinned_host(payload_buf)};
         Device &D = *ctx->devs[0];
         int rc = compress_on_device(D, samples, dev_ptr, frame_off, frame_len, idx.data(), n_frames, compressor,
                                     max_error, speed, bounded, out, sink);
@@ -795,7 +821,7 @@ int atsc_gpu_compress_frames(atsc_ctx *ctx, const double *samples, const uint64_
         uint64_t cap = 0;
         for (uint32_t i : parts[d]) cap += (uint64_t)frame_len[i] * 16 + 64;  // worst case: RLE of all-distinct f64
         bufs[d].resize(cap);
-        sinks[d] = PayloadSink{bufs[d].data(), cap, 0, false};
+        sinks[d] = PayloadSink{bufs[d].data(), cap, 0, false, false};
         th.emplace_back([&, d]() {
             if (parts[d].empty()) return;
             rcs[d] = compress_on_device(*ctx->devs[d], samples, false, frame_off, frame_len, parts[d].data(),

@@ -16,10 +16,19 @@
 
 namespace atsc {
 
+constexpr int FFT_THREADS = 512;                                // CTA size of the FFT kernels: 2 CTAs per SM
+constexpr int FFT_LANES = 16;                                   // transforms side by side in one tile
+constexpr int FFT_SUB = 32 / FFT_LANES;                         // butterfly slots per warp
+constexpr int FFT_SLOTS = (FFT_THREADS / 32) * FFT_SUB;         // butterfly slots per CTA (32: FftStage.dp/dq)
 constexpr int FFT_TLEN = 320;                                   // max sub-FFT length
-constexpr int FFT_FP = 33;                                      // padded batch stride (float2 units)
+constexpr int FFT_FP = FFT_LANES + 1;                           // padded batch stride (float2 units)
 constexpr int FFT_TILE_F2 = FFT_TLEN * FFT_FP;                  // float2 per tile buffer
-constexpr int FFT_SMEM_BYTES = 2 * FFT_TILE_F2 * (int)sizeof(float2);  // 168,960 B
+constexpr int FFT_SMEM_BYTES = 2 * FFT_TILE_F2 * (int)sizeof(float2);  // 87,040 B -> two CTAs per SM
+constexpr int FFT_SORT_CAP = 8192;                              // u64 entries the tile buffers can sort at once
+
+// thread -> (butterfly slot, transform lane) of a tile
+__device__ inline int fft_lane() { return threadIdx.x & (FFT_LANES - 1); }
+__device__ inline int fft_slot() { return (threadIdx.x >> 5) * FFT_SUB + ((threadIdx.x & 31) / FFT_LANES); }
 constexpr int FFT_KCAP = 16384;                                 // max list entries when compressing (pow2 for the sort)
 constexpr int FFT_DEC_KCAP = 65536;                             // max entries accepted when decoding (pos is a u16)
 constexpr int FFT_SCHED = 23;                                   // fft.rs:348-352
@@ -68,83 +77,174 @@ __device__ inline float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x
 __device__ inline float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
 // ---------------------------------------------------------------------------------------
+// small DFTs in registers (checked against np.fft in tools/radix_check.py)
+// ---------------------------------------------------------------------------------------
+template <bool INV>
+__device__ inline float2 mul_i(float2 v) {  // v * (+i) for the inverse, v * (-i) for the forward transform
+    return INV ? make_float2(-v.y, v.x) : make_float2(v.y, -v.x);
+}
+template <bool INV>
+__device__ inline void dft3(float2 &a0, float2 &a1, float2 &a2) {
+    const float c = 0.86602540378443864676f;
+    float2 t = cadd(a1, a2), d = csub(a1, a2);
+    float2 m = make_float2(a0.x - 0.5f * t.x, a0.y - 0.5f * t.y);
+    float2 rot = mul_i<INV>(make_float2(c * d.x, c * d.y));
+    a0 = cadd(a0, t);
+    a1 = cadd(m, rot);
+    a2 = csub(m, rot);
+}
+template <bool INV>
+__device__ inline void dft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3) {
+    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_i<INV>(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    a2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+template <bool INV>
+__device__ inline void dft8(float2 *a) {  // in place, natural order out
+    const float r = 0.70710678118654752440f;
+    float2 l0 = cadd(a[0], a[4]), l1 = cadd(a[1], a[5]), l2 = cadd(a[2], a[6]), l3 = cadd(a[3], a[7]);
+    float2 h0 = csub(a[0], a[4]), h1 = csub(a[1], a[5]), h2 = csub(a[2], a[6]), h3 = csub(a[3], a[7]);
+    // h_j *= W8^j : W8 = exp(-+ i pi/4)
+    float2 i1 = mul_i<INV>(h1), i3 = mul_i<INV>(h3);
+    h1 = make_float2(r * (h1.x + i1.x), r * (h1.y + i1.y));
+    h2 = mul_i<INV>(h2);
+    h3 = make_float2(r * (i3.x - h3.x), r * (i3.y - h3.y));
+    dft4<INV>(l0, l1, l2, l3);
+    dft4<INV>(h0, h1, h2, h3);
+    a[0] = l0;
+    a[1] = h0;
+    a[2] = l1;
+    a[3] = h1;
+    a[4] = l2;
+    a[5] = h2;
+    a[6] = l3;
+    a[7] = h3;
+}
+template <bool INV>
+__device__ inline void dft9(float2 *a) {  // in place, natural order out
+    // W9^k = exp(-+ 2 pi i k / 9)
+    const float c1 = 0.76604444311897803520f, s1 = 0.64278760968653932632f;
+    const float c2 = 0.17364817766693034885f, s2 = 0.98480775301220805937f;
+    const float c4 = -0.93969262078590838405f, s4 = 0.34202014332566873304f;
+    const float2 w1 = make_float2(c1, INV ? s1 : -s1), w2 = make_float2(c2, INV ? s2 : -s2),
+                 w4 = make_float2(c4, INV ? s4 : -s4);
+    dft3<INV>(a[0], a[3], a[6]);  // t[0][k1] in a[0], a[3], a[6]
+    dft3<INV>(a[1], a[4], a[7]);  // t[1][k1]
+    dft3<INV>(a[2], a[5], a[8]);  // t[2][k1]
+    a[4] = cmul(a[4], w1);
+    a[7] = cmul(a[7], w2);
+    a[5] = cmul(a[5], w2);
+    a[8] = cmul(a[8], w4);
+    dft3<INV>(a[0], a[1], a[2]);  // k1 = 0 -> y[0], y[3], y[6]
+    dft3<INV>(a[3], a[4], a[5]);  // k1 = 1 -> y[1], y[4], y[7]
+    dft3<INV>(a[6], a[7], a[8]);  // k1 = 2 -> y[2], y[5], y[8]
+    float2 y1 = a[3], y2 = a[6], y3 = a[1], y5 = a[7], y6 = a[2], y7 = a[5];
+    a[1] = y1;
+    a[2] = y2;
+    a[3] = y3;
+    a[5] = y5;
+    a[6] = y6;
+    a[7] = y7;
+}
+
+// One Stockham DIF stage of radix R for the 32 transforms of a tile.
+//   y[q + s*(R*p + u)] = DFT_R(x[q + s*(p + t*m)], t < R)[u] * W_n^{p*u}
+// LAST: the stage's own twiddles are all 1 (m == 1).  FUSE (only with LAST): multiply the result
+// element e by the four-step twiddle W_M^{+-(e*(base+lane))} = twM[e*base] * twEF[e][lane].
+template <int R, bool INV, bool LAST, bool FUSE>
+__device__ inline void fft_stage(const float2 *x, float2 *y, const FftStage S, const float2 *__restrict__ tw,
+                                 int nb, uint32_t base, const float2 *__restrict__ twM,
+                                 const float2 *__restrict__ twEF) {
+    const int warp = fft_slot(), lane = fft_lane(), nw = FFT_SLOTS;
+    const int m = S.m, s = S.s, tws = S.tws, nbf = S.nbf;
+    if (lane >= nb) return;
+    int p = (warp * (int)S.magic) >> 16, q = warp - p * s;
+    const int dp = S.dp, dq = S.dq;
+    const int xs = s * m * FFT_FP, ys = s * FFT_FP;
+    for (int b = warp; b < nbf; b += nw, p += dp, q += dq) {
+        if (q >= s) {
+            q -= s;
+            p++;
+        }
+        const float2 *xi = x + (q + s * p) * FFT_FP + lane;
+        float2 a[R];
+#pragma unroll
+        for (int t = 0; t < R; t++) a[t] = xi[t * xs];
+        if (R == 2) {
+            float2 t0 = cadd(a[0], a[1]);
+            a[1] = csub(a[0], a[1]);
+            a[0] = t0;
+        } else if (R == 3) {
+            dft3<INV>(a[0], a[1], a[2]);
+        } else if (R == 4) {
+            dft4<INV>(a[0], a[1], a[2], a[3]);
+        } else if (R == 8) {
+            dft8<INV>(a);
+        } else {
+            dft9<INV>(a);
+        }
+        const int eo = q + s * R * p;  // output element of leg 0
+        float2 *yo = y + eo * FFT_FP + lane;
+        if (!LAST) {
+#pragma unroll
+            for (int u = 1; u < R; u++) {
+                float2 w = tw[u * p * tws];
+                a[u] = INV ? cmulc(a[u], w) : cmul(a[u], w);
+            }
+        }
+        if (FUSE) {
+#pragma unroll
+            for (int u = 0; u < R; u++) {
+                const int e = eo + u * s;
+                float2 w = cmul(twM[(uint32_t)e * base], twEF[e * 32 + lane]);
+                a[u] = INV ? cmulc(a[u], w) : cmul(a[u], w);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < R; u++) yo[u * ys] = a[u];
+    }
+}
+
+template <bool INV, bool LAST, bool FUSE>
+__device__ inline void fft_stage_any(const float2 *x, float2 *y, const FftStage S, const float2 *__restrict__ tw,
+                                     int nb, uint32_t base, const float2 *__restrict__ twM,
+                                     const float2 *__restrict__ twEF) {
+    switch (S.r) {
+        case 2: fft_stage<2, INV, LAST, FUSE>(x, y, S, tw, nb, base, twM, twEF); break;
+        case 3: fft_stage<3, INV, LAST, FUSE>(x, y, S, tw, nb, base, twM, twEF); break;
+        case 4: fft_stage<4, INV, LAST, FUSE>(x, y, S, tw, nb, base, twM, twEF); break;
+        case 8: fft_stage<8, INV, LAST, FUSE>(x, y, S, tw, nb, base, twM, twEF); break;
+        default: fft_stage<9, INV, LAST, FUSE>(x, y, S, tw, nb, base, twM, twEF); break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // 32-wide batched Stockham DIF FFT of length `len` in shared memory.
 // Element e of transform f lives at x[e*FFT_FP + f].  Returns the buffer with the result.
+// twM != nullptr: the four-step twiddle (see fft_stage) is fused into the last stage.
 // ---------------------------------------------------------------------------------------
 template <bool INV>
 __device__ inline float2 *tile_fft(float2 *x, float2 *y, int len, const FftStage *stg, int ns,
-                                   const float2 *__restrict__ tw, int nb) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+                                   const float2 *__restrict__ tw, int nb, uint32_t base = 0,
+                                   const float2 *__restrict__ twM = nullptr,
+                                   const float2 *__restrict__ twEF = nullptr) {
     (void)len;
     for (int st = 0; st < ns; st++) {
         const FftStage S = stg[st];
-        const int r = S.r, m = S.m, s = S.s, tws = S.tws, nbf = S.nbf;
-        if (lane < nb) {
-            // butterfly b = p * s + q; (p, q) advance incrementally (nw = 32 warps)
-            int p = (warp * (int)S.magic) >> 16, q = warp - p * s;
-            const int dp = S.dp, dq = S.dq;
-            for (int b = warp; b < nbf; b += nw, p += dp, q += dq) {
-                if (q >= s) {
-                    q -= s;
-                    p++;
-                }
-                const float2 *xi = x + (q + s * p) * FFT_FP + lane;
-                float2 *yo = y + (q + s * r * p) * FFT_FP + lane;
-                const int xs = s * m * FFT_FP;  // input stride between radix legs
-                const int ys = s * FFT_FP;      // output stride between radix legs
-                if (r == 4) {
-                    float2 a0 = xi[0], a1 = xi[xs], a2 = xi[2 * xs], a3 = xi[3 * xs];
-                    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
-                    // forward: -i*t3 ; inverse: +i*t3
-                    float2 jt3 = INV ? make_float2(-t3.y, t3.x) : make_float2(t3.y, -t3.x);
-                    float2 b0 = cadd(t0, t2), b1 = cadd(t1, jt3), b2 = csub(t0, t2), b3 = csub(t1, jt3);
-                    float2 w1 = tw[p * tws], w2 = tw[2 * p * tws], w3 = tw[3 * p * tws];
-                    yo[0] = b0;
-                    yo[ys] = INV ? cmulc(b1, w1) : cmul(b1, w1);
-                    yo[2 * ys] = INV ? cmulc(b2, w2) : cmul(b2, w2);
-                    yo[3 * ys] = INV ? cmulc(b3, w3) : cmul(b3, w3);
-                } else if (r == 3) {
-                    float2 a0 = xi[0], a1 = xi[xs], a2 = xi[2 * xs];
-                    float2 t = cadd(a1, a2), d = csub(a1, a2);
-                    float2 mm = make_float2(a0.x - 0.5f * t.x, a0.y - 0.5f * t.y);
-                    const float c = 0.86602540378443864676f;
-                    float2 rot = INV ? make_float2(-c * d.y, c * d.x) : make_float2(c * d.y, -c * d.x);
-                    float2 b0 = cadd(a0, t), b1 = cadd(mm, rot), b2 = csub(mm, rot);
-                    float2 w1 = tw[p * tws], w2 = tw[2 * p * tws];
-                    yo[0] = b0;
-                    yo[ys] = INV ? cmulc(b1, w1) : cmul(b1, w1);
-                    yo[2 * ys] = INV ? cmulc(b2, w2) : cmul(b2, w2);
-                } else {  // r == 2
-                    float2 a0 = xi[0], a1 = xi[xs];
-                    float2 w1 = tw[p * tws];
-                    float2 b1 = csub(a0, a1);
-                    yo[0] = cadd(a0, a1);
-                    yo[ys] = INV ? cmulc(b1, w1) : cmul(b1, w1);
-                }
-            }
-        }
+        if (st + 1 < ns)
+            fft_stage_any<INV, false, false>(x, y, S, tw, nb, base, twM, twEF);
+        else if (twM)
+            fft_stage_any<INV, true, true>(x, y, S, tw, nb, base, twM, twEF);
+        else
+            fft_stage_any<INV, true, false>(x, y, S, tw, nb, base, twM, twEF);
         __syncthreads();
         float2 *t = x;
         x = y;
         y = t;
     }
     return x;
-}
-
-// multiply tile element (e, f) by W_M^{+-(e * (base + f))} = twM[e*base] * twEF[e][f]
-template <bool INV>
-__device__ inline void tile_twiddle(float2 *x, int len, int nb, uint32_t base,
-                                    const float2 *__restrict__ twM,
-                                    const float2 *__restrict__ twEF) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    if (lane < nb) {
-        for (int e = warp; e < len; e += nw) {
-            float2 w = cmul(twM[(uint32_t)e * base], twEF[e * 32 + lane]);
-            float2 v = x[e * FFT_FP + lane];
-            x[e * FFT_FP + lane] = INV ? cmulc(v, w) : cmul(v, w);
-        }
-    }
-    __syncthreads();
 }
 
 // rows r0..r0+nb-1 of the [M1][M2] global matrix <-> tile (element = column index)
@@ -166,13 +266,13 @@ __device__ inline void tile_store_rows(const float2 *x, float2 *__restrict__ W, 
 }
 // columns c0..c0+nb-1 (element = row index)
 __device__ inline void tile_load_cols(float2 *x, const float2 *__restrict__ W, int M1, int M2, int c0, int nb) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int warp = fft_slot(), lane = fft_lane(), nw = FFT_SLOTS;
     if (lane < nb)
         for (int e = warp; e < M1; e += nw) x[e * FFT_FP + lane] = W[(size_t)e * M2 + c0 + lane];
     __syncthreads();
 }
 __device__ inline void tile_store_cols(const float2 *x, float2 *__restrict__ W, int M1, int M2, int c0, int nb) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int warp = fft_slot(), lane = fft_lane(), nw = FFT_SLOTS;
     if (lane < nb)
         for (int e = warp; e < M1; e += nw) W[(size_t)e * M2 + c0 + lane] = x[e * FFT_FP + lane];
     __syncthreads();
@@ -191,7 +291,7 @@ __device__ inline double padded_sample(const double *__restrict__ d, uint32_t N,
 __device__ inline void prefetch_col_tile(const double *__restrict__ d, uint32_t N, uint32_t prefix, int M1, int M2,
                                          int c0, int real) {
     if (c0 >= M2) return;
-    const int per_row = real ? 4 : 2;  // 128-byte lines per row: 32 columns x (2 or 1) doubles
+    const int per_row = (FFT_LANES * (real ? 2 : 1) * 8 + 127) / 128;  // 128-byte lines per row of the tile
     for (int i = threadIdx.x; i < M1 * per_row; i += blockDim.x) {
         int e = i / per_row, ln = i - e * per_row;
         uint32_t n = (uint32_t)e * M2 + c0;
@@ -208,11 +308,11 @@ __device__ inline void fft_forward(const double *__restrict__ d, uint32_t N, uin
                                    const FftGeom &g, FftWs ws, float2 *sm) {
     float2 *bufA = sm, *bufB = sm + FFT_TILE_F2;
     const int M1 = g.M1, M2 = g.M2;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int warp = fft_slot(), lane = fft_lane(), nw = FFT_SLOTS;
     // pass 1: column tiles; input built from the samples
-    for (int c0 = 0; c0 < M2; c0 += 32) {
-        int nb = min(32, M2 - c0);
-        prefetch_col_tile(d, N, prefix, M1, M2, c0 + 32, g.real);
+    for (int c0 = 0; c0 < M2; c0 += FFT_LANES) {
+        int nb = min(FFT_LANES, M2 - c0);
+        prefetch_col_tile(d, N, prefix, M1, M2, c0 + FFT_LANES, g.real);
         if (lane < nb) {
             for (int e = warp; e < M1; e += nw) {
                 uint32_t n = (uint32_t)e * M2 + c0 + lane;
@@ -228,13 +328,12 @@ __device__ inline void fft_forward(const double *__restrict__ d, uint32_t N, uin
             }
         }
         __syncthreads();
-        float2 *res = tile_fft<false>(bufA, bufB, M1, g.st1, g.ns1, g.tw1, nb);
-        tile_twiddle<false>(res, M1, nb, (uint32_t)c0, g.twM, g.twA);
+        float2 *res = tile_fft<false>(bufA, bufB, M1, g.st1, g.ns1, g.tw1, nb, (uint32_t)c0, g.twM, g.twA);
         tile_store_cols(res, ws.W, M1, M2, c0, nb);
     }
     // pass 2: row tiles, in place
-    for (int r0 = 0; r0 < M1; r0 += 32) {
-        int nb = min(32, M1 - r0);
+    for (int r0 = 0; r0 < M1; r0 += FFT_LANES) {
+        int nb = min(FFT_LANES, M1 - r0);
         tile_load_rows(bufA, ws.W, M2, r0, nb);
         float2 *res = tile_fft<false>(bufA, bufB, M2, g.st2, g.ns2, g.tw2, nb);
         tile_store_rows(res, ws.W, M2, r0, nb);
@@ -295,10 +394,10 @@ __device__ inline uint32_t fft_bin_of(uint32_t i, uint32_t pM, uint32_t pM1, uin
 // ---------------------------------------------------------------------------------------
 __device__ inline void find_digit(const uint32_t *hist, uint32_t nbins, uint32_t remaining, uint32_t *sh,
                                   uint32_t *d, uint32_t *above, uint32_t *cnt) {
-    const uint32_t t = threadIdx.x, per = nbins >= blockDim.x ? nbins / blockDim.x : 1;
-    uint32_t loc[4], sum = 0;
+    const uint32_t t = threadIdx.x, per = nbins >= blockDim.x ? nbins / blockDim.x : 1;  // <= 8
+    uint32_t loc[8], sum = 0;
 #pragma unroll
-    for (uint32_t j = 0; j < 4; j++) {
+    for (uint32_t j = 0; j < 8; j++) {
         uint32_t pos = t * per + j;  // position in descending-digit order
         loc[j] = (j < per && pos < nbins) ? hist[nbins - 1 - pos] : 0u;
         sum += loc[j];
@@ -308,7 +407,7 @@ __device__ inline void find_digit(const uint32_t *hist, uint32_t nbins, uint32_t
     if (excl < remaining && remaining <= excl + sum) {
         uint32_t acc = excl;
 #pragma unroll
-        for (uint32_t j = 0; j < 4; j++) {
+        for (uint32_t j = 0; j < 8; j++) {
             if (j < per && acc < remaining && remaining <= acc + loc[j]) {
                 sh[102] = nbins - 1 - (t * per + j);
                 sh[103] = acc;
@@ -324,69 +423,46 @@ __device__ inline void find_digit(const uint32_t *hist, uint32_t nbins, uint32_t
     __syncthreads();
 }
 
-// ---------------------------------------------------------------------------------------
-// top-K of the half spectrum by |z| (fft.rs:231-257), descending, ties by lower bin.
-// Writes list[0..K) and returns K = min(kmax, #nonzero bins).  (pM, pM1, pM2) describe the
-// storage order of ws.keys (pM = 0: natural order).  sm64 must hold FFT_KCAP u64.
-//
-// Two 12-bit histogram passes fix the top 24 bits of the K-th largest key; every key at or
-// above that 24-bit bucket is compacted (a few more than K), sorted, and the first K kept.
-// Only when the boundary bucket is so crowded that the candidates would not fit does a third
-// pass resolve the low 8 bits exactly.
-// ---------------------------------------------------------------------------------------
-__device__ inline uint32_t fft_topk(uint32_t Bn, FftWs ws, uint32_t kmax, FftEntry *list,
-                                    unsigned long long *sm64, uint32_t *sh, bool *tie_at_cut,
-                                    uint32_t pM, uint32_t pM1, uint32_t pM2) {
-    const uint32_t T = blockDim.x, t = threadIdx.x;
-    uint32_t *hist = (uint32_t *)sm64;  // 4096 bins (phase-local reuse of the big smem region)
-    *tie_at_cut = false;
-    // ---- level 1: top 12 bits (+ count of zero bins)
-    for (uint32_t i = t; i < 4096; i += T) hist[i] = 0;
-    __syncthreads();
+// sort key of a spectrum bin: |z| (f32 bits) descending, then bin ascending; unique per bin
+__device__ inline unsigned long long fft_composite(uint32_t key, uint32_t bin) {
+    return ((unsigned long long)key << 20) | (unsigned long long)(0xFFFFFu - bin);
+}
+
+// number of bins with a non-zero |z| (fft_trim stops at the first exact zero, fft.rs:249-252)
+__device__ inline uint32_t fft_count_nonzero(uint32_t Bn, FftWs ws, uint32_t *sh) {
     uint32_t zeros = 0;
-    for (uint32_t b0 = t; b0 < Bn; b0 += 4 * T) {
-        uint32_t k[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) k[u] = (b0 + u * T < Bn) ? ws.keys[b0 + u * T] : 0xFFFFFFFFu;
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (k[u] != 0xFFFFFFFFu) {
-                zeros += k[u] == 0u;
-                atomicAdd(&hist[k[u] >> 20], 1u);
-            }
-    }
-    const uint32_t nz = Bn - block_sum_u32(zeros, sh);
-    const uint32_t K = min(min(kmax, nz), (uint32_t)FFT_KCAP);
-    if (K == 0) return 0;
-    uint32_t d1, above1, cnt1;
-    find_digit(hist, 4096, K, sh, &d1, &above1, &cnt1);
-    uint32_t remaining = K - above1;
-    // ---- level 2: next 12 bits inside bucket d1
-    for (uint32_t i = t; i < 4096; i += T) hist[i] = 0;
-    __syncthreads();
-    for (uint32_t b0 = t; b0 < Bn; b0 += 4 * T) {
-        uint32_t k[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) k[u] = (b0 + u * T < Bn) ? ws.keys[b0 + u * T] : 0xFFFFFFFFu;
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (k[u] != 0xFFFFFFFFu && (k[u] >> 20) == d1) atomicAdd(&hist[(k[u] >> 8) & 0xFFFu], 1u);
-    }
-    __syncthreads();
-    uint32_t d2, above2, cnt2;
-    find_digit(hist, 4096, remaining, sh, &d2, &above2, &cnt2);
-    remaining -= above2;  // how many of the cnt2 keys in the boundary bucket belong to the top K
-    const uint32_t T24 = (d1 << 12) | d2;
-    const uint32_t Kover = K - remaining + cnt2;  // candidates if the whole bucket is taken
-    uint32_t Pover = 1;
-    while (Pover < Kover) Pover <<= 1;
-    unsigned long long *S = sm64;
-    uint32_t nsel = K, P;
-    bool tie = false;
-    __syncthreads();
-    if (Pover <= (uint32_t)FFT_KCAP) {
-        // ---- over-select: all keys whose top 24 bits are >= T24 (unordered; the sort orders them)
-        if (t == 0) sh[107] = 0;
+    for (uint32_t b = threadIdx.x; b < Bn; b += blockDim.x) zeros += ws.keys[b] == 0u;
+    return Bn - block_sum_u32(zeros, sh);
+}
+
+// ---------------------------------------------------------------------------------------
+// top-k of the half spectrum by |z| (fft.rs:231-257): writes the entries of rank
+// [done, done + want) in descending (|z|, then lower bin) order to list[done ..].
+//   Cprev  : composite of entry done-1 (~0 for the first chunk); *Clast <- composite of the last one
+//   (pM, pM1, pM2): storage order of ws.keys (pM = 0: natural order)
+// A radix select over the 52-bit composite (12-bit digits) narrows the bucket that holds rank
+// done+want until "everything at or above that bucket" fits the shared-memory sort; those
+// candidates are compacted (unordered), bitonic-sorted, and the first `want` kept.
+// Returns true if equal |z| values sit on both sides of the final cut (BinaryHeap pops equal
+// norms in unspecified order -> near-tie).
+// ---------------------------------------------------------------------------------------
+__device__ inline bool fft_topk_chunk(uint32_t Bn, FftWs ws, uint32_t done, uint32_t want, unsigned long long Cprev,
+                                      FftEntry *list, unsigned long long *sm64, uint32_t *sh, uint32_t pM,
+                                      uint32_t pM1, uint32_t pM2, unsigned long long *Clast) {
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    uint32_t *hist = (uint32_t *)sm64;  // <= 4096 bins (phase-local reuse of the tile buffers)
+    const uint32_t target = done + want;
+    unsigned long long prefix = 0;
+    uint32_t remaining = target;
+    int shift = 52;
+    // ---- radix select on the composite
+    const int shifts[5] = {40, 28, 16, 4, 0};
+    for (int lv = 0; lv < 5; lv++) {
+        const int bits = lv == 4 ? 4 : 12;
+        const uint32_t nbins = 1u << bits;
+        const int hi_shift = shift;  // bits above this are already fixed to `prefix`
+        shift = shifts[lv];
+        for (uint32_t i = t; i < nbins; i += T) hist[i] = 0;
         __syncthreads();
         for (uint32_t b0 = t; b0 < Bn; b0 += 4 * T) {
             uint32_t k[4];
@@ -394,59 +470,50 @@ __device__ inline uint32_t fft_topk(uint32_t Bn, FftWs ws, uint32_t kmax, FftEnt
             for (int u = 0; u < 4; u++) k[u] = (b0 + u * T < Bn) ? ws.keys[b0 + u * T] : 0u;
 #pragma unroll
             for (int u = 0; u < 4; u++)
-                if (k[u] != 0u && (k[u] >> 8) >= T24) {
-                    uint32_t pos = atomicAdd(&sh[107], 1u);
-                    uint32_t bin = fft_bin_of(b0 + u * T, pM, pM1, pM2);
-                    if (pos < (uint32_t)FFT_KCAP)
-                        S[pos] = ((unsigned long long)k[u] << 32) | ((unsigned long long)(0xFFFFFu - bin) << 12);
+                if (k[u] != 0u) {
+                    uint32_t bin = shift < 20 ? fft_bin_of(b0 + u * T, pM, pM1, pM2) : 0u;
+                    unsigned long long c = fft_composite(k[u], bin);
+                    if (hi_shift >= 52 || (c >> hi_shift) == prefix) atomicAdd(&hist[(uint32_t)(c >> shift) & (nbins - 1)], 1u);
                 }
         }
         __syncthreads();
-        nsel = min(sh[107], (uint32_t)FFT_KCAP);
-        P = 1;
-        while (P < nsel) P <<= 1;
-    } else {
-        // ---- crowded boundary bucket: resolve the low 8 bits, then take exactly K
-        for (uint32_t i = t; i < 256; i += T) hist[i] = 0;
-        __syncthreads();
-        for (uint32_t b = t; b < Bn; b += T) {
-            uint32_t key = ws.keys[b];
-            if ((key >> 8) == T24) atomicAdd(&hist[key & 255u], 1u);
-        }
-        __syncthreads();
-        uint32_t d3, above3, eq_total;
-        find_digit(hist, 256, remaining, sh, &d3, &above3, &eq_total);
-        const uint32_t take_eq = remaining - above3;
-        const uint32_t Tkey = (T24 << 8) | d3;
-        tie = eq_total > take_eq;
-        P = 1;
-        while (P < K) P <<= 1;
-        // equal |z| may straddle the cut: take the lowest array indices first (ordered compaction)
-        uint32_t base = 0, eqbase = 0;
-        for (uint32_t b0 = 0; b0 < Bn; b0 += T) {
-            uint32_t b = b0 + t;
-            uint32_t key = b < Bn ? ws.keys[b] : 0u;
-            bool gt = b < Bn && key > Tkey;
-            bool eq = b < Bn && key == Tkey;
-            uint32_t eqtot;
-            uint32_t eqrank = eqbase + block_excl_scan_u32(eq ? 1u : 0u, sh, &eqtot);
-            __syncthreads();
-            bool sel = gt || (eq && eqrank < take_eq);
-            uint32_t tot;
-            uint32_t pos = base + block_excl_scan_u32(sel ? 1u : 0u, sh, &tot);
-            if (sel) {
-                uint32_t bin = fft_bin_of(b, pM, pM1, pM2);
-                S[pos] = ((unsigned long long)key << 32) | ((unsigned long long)(0xFFFFFu - bin) << 12);
-            }
-            base += tot;
-            eqbase += eqtot;
-            __syncthreads();
-        }
-        nsel = K;
+        uint32_t dsel, above, cnt;
+        find_digit(hist, nbins, remaining, sh, &dsel, &above, &cnt);
+        remaining -= above;
+        prefix = (prefix << bits) | dsel;
+        // candidates if the whole bucket is taken = (#composites above the bucket) + cnt - done
+        uint32_t ncand = (target - remaining) + cnt - done;
+        uint32_t P = 1;
+        while (P < ncand) P <<= 1;
+        if (P <= (uint32_t)FFT_SORT_CAP) break;
     }
+    const unsigned long long Tlow = prefix << shift;  // smallest composite of the boundary bucket
+    // ---- compaction (unordered; the sort orders it)
+    unsigned long long *S = sm64;
+    __syncthreads();
+    if (t == 0) sh[107] = 0;
+    __syncthreads();
+    for (uint32_t b0 = t; b0 < Bn; b0 += 4 * T) {
+        uint32_t k[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) k[u] = (b0 + u * T < Bn) ? ws.keys[b0 + u * T] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (k[u] != 0u) {
+                unsigned long long c = fft_composite(k[u], fft_bin_of(b0 + u * T, pM, pM1, pM2));
+                if (c >= Tlow && c < Cprev) {
+                    uint32_t pos = atomicAdd(&sh[107], 1u);
+                    if (pos < (uint32_t)FFT_SORT_CAP) S[pos] = c;
+                }
+            }
+    }
+    __syncthreads();
+    const uint32_t nsel = min(sh[107], (uint32_t)FFT_SORT_CAP);
+    uint32_t P = 1;
+    while (P < nsel) P <<= 1;
     for (uint32_t i = nsel + t; i < P; i += T) S[i] = 0ull;
     __syncthreads();
-    // bitonic sort, descending: (|z| desc, bin asc)
+    // ---- bitonic sort, descending
     for (uint32_t k2 = 2; k2 <= P; k2 <<= 1) {
         for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
             for (uint32_t i = t; i < P; i += T) {
@@ -463,29 +530,73 @@ __device__ inline uint32_t fft_topk(uint32_t Bn, FftWs ws, uint32_t kmax, FftEnt
             __syncthreads();
         }
     }
-    // equal |z| on both sides of the K cut?
-    if (nsel > K && (uint32_t)(S[K - 1] >> 32) == (uint32_t)(S[K] >> 32)) tie = true;
-    for (uint32_t r = t; r < K; r += T) {
-        uint32_t bin = 0xFFFFFu - (uint32_t)((S[r] >> 12) & 0xFFFFFull);
-        // array index of this bin (inverse of fft_bin_of)
-        uint32_t i = bin;
+    const uint32_t take = min(want, nsel);
+    for (uint32_t r = t; r < take; r += T) {
+        uint32_t bin = 0xFFFFFu - (uint32_t)(S[r] & 0xFFFFFull);
+        uint32_t i = bin;  // array index of this bin (inverse of fft_bin_of)
         if (pM && bin < pM) i = (bin % pM1) * pM2 + bin / pM1;
         float2 X = ws.Xd[i];
         FftEntry e;
         e.bin = bin;
         e.re = X.x;
         e.im = X.y;
-        list[r] = e;
+        list[done + r] = e;
     }
-    *tie_at_cut = tie;
+    *Clast = take ? S[take - 1] : Cprev;
+    // equal |z| on both sides of the cut?  (the whole boundary bucket was taken, so the next
+    // candidate is visible whenever one with the same top bits exists)
+    bool tie = take > 0 && nsel > take && (S[take - 1] >> 20) == (S[take] >> 20);
+    if (take > 0 && nsel == take) {
+        // nothing beyond the cut among the candidates: look for an equal key below the bucket
+        const uint32_t kcut = (uint32_t)(S[take - 1] >> 20);
+        uint32_t eq = 0;
+        for (uint32_t b = t; b < Bn; b += T) eq += ws.keys[b] == kcut;
+        uint32_t eq_all = block_sum_u32(eq, sh);
+        uint32_t eq_sel = 0;
+        for (uint32_t r = t; r < take; r += T) eq_sel += (uint32_t)(S[r] >> 20) == kcut;
+        // entries of earlier chunks with the same key are above the cut as well
+        for (uint32_t r = t; r < done; r += T) {
+            uint32_t bin = list[r].bin, i = bin;
+            if (pM && bin < pM) i = (bin % pM1) * pM2 + bin / pM1;
+            eq_sel += ws.keys[i] == kcut;
+        }
+        uint32_t eq_in = block_sum_u32(eq_sel, sh);
+        tie = eq_all > eq_in;
+    }
     __syncthreads();
+    return tie;
+}
+
+// builds list[0..K) for K = min(kmax, nonzero bins) in chunks the shared-memory sort can hold;
+// cut_tie[i] (i < ncuts) tells whether a cut after cuts[i] entries separates equal |z|.
+// Returns K.  After the call sm64 holds the LAST chunk only.
+__device__ inline uint32_t fft_topk(uint32_t Bn, FftWs ws, uint32_t kmax, FftEntry *list,
+                                    unsigned long long *sm64, uint32_t *sh, bool *tie_at_cut,
+                                    uint32_t pM, uint32_t pM1, uint32_t pM2) {
+    const uint32_t nz = fft_count_nonzero(Bn, ws, sh);
+    const uint32_t K = min(min(kmax, nz), (uint32_t)FFT_KCAP);
+    *tie_at_cut = false;
+    if (K == 0) return 0;
+    constexpr uint32_t CHUNK = FFT_SORT_CAP / 2 + FFT_SORT_CAP / 4;  // leaves room for the over-selected bucket
+    uint32_t done = 0;
+    unsigned long long Cprev = ~0ull;
+    while (done < K) {
+        uint32_t want = min(K - done, CHUNK);
+        unsigned long long Clast;
+        bool tie = fft_topk_chunk(Bn, ws, done, want, Cprev, list, sm64, sh, pM, pM1, pM2, &Clast);
+        done += want;
+        Cprev = Clast;
+        if (done >= K) *tie_at_cut = tie;
+    }
     return K;
 }
 
-// after fft_topk: S (sm64) still holds the sorted composite keys; true if a cut after the
-// first c entries separates two bins with equal |z|
-__device__ inline bool fft_cut_splits_tie(const unsigned long long *S, uint32_t c, uint32_t K) {
-    return c > 0 && c < K && (uint32_t)(S[c - 1] >> 32) == (uint32_t)(S[c] >> 32);
+// equal |z| on both sides of a cut after the first c list entries (c < K)?
+__device__ inline bool fft_cut_splits_tie_list(const FftEntry *list, uint32_t c, uint32_t K) {
+    if (c == 0 || c >= K) return false;
+    FftEntry a = list[c - 1], b = list[c];
+    double na = sqrt((double)a.re * a.re + (double)a.im * a.im), nb = sqrt((double)b.re * b.re + (double)b.im * b.im);
+    return (float)na == (float)nb;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -563,11 +674,11 @@ __device__ inline void fft_inverse(const FftGeom &g, FftWs ws, uint32_t c, float
                                    const double *pf_d = nullptr, uint32_t pf_N = 0, uint32_t pf_prefix = 0) {
     float2 *bufA = sm, *bufB = sm + FFT_TILE_F2;
     const int M1 = g.M1, M2 = g.M2;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int warp = fft_slot(), lane = fft_lane(), nw = FFT_SLOTS;
     const uint32_t T = blockDim.x, t = threadIdx.x;
     // pass 1: row tiles built from the sparse list
-    for (int r0 = 0; r0 < M1; r0 += 32) {
-        int nb = min(32, M1 - r0);
+    for (int r0 = 0; r0 < M1; r0 += FFT_LANES) {
+        int nb = min(FFT_LANES, M1 - r0);
         for (uint32_t i = t; i < (uint32_t)M2 * FFT_FP; i += T) bufA[i] = make_float2(0.f, 0.f);
         __syncthreads();
         for (uint32_t r = t; r < c; r += T) {
@@ -576,7 +687,7 @@ __device__ inline void fft_inverse(const FftGeom &g, FftWs ws, uint32_t c, float
             uint32_t l = ws.locD[r];
             if (l != 0xFFFFFFFFu) {
                 uint32_t f = (l >> 16) - (uint32_t)r0;
-                if (f < 32u) bufA[(l & 0xFFFFu) * FFT_FP + f] = ws.cD[r];
+                if (f < (uint32_t)FFT_LANES) bufA[(l & 0xFFFFu) * FFT_FP + f] = ws.cD[r];
             }
         }
         __syncthreads();
@@ -586,24 +697,23 @@ __device__ inline void fft_inverse(const FftGeom &g, FftWs ws, uint32_t c, float
             uint32_t l = ws.locM[r];
             if (l != 0xFFFFFFFFu) {
                 uint32_t f = (l >> 16) - (uint32_t)r0;
-                if (f < 32u) {
+                if (f < (uint32_t)FFT_LANES) {
                     float2 *q = &bufA[(l & 0xFFFFu) * FFT_FP + f];
                     *q = cadd(*q, ws.cM[r]);
                 }
             }
         }
         __syncthreads();
-        float2 *res = tile_fft<true>(bufA, bufB, M2, g.st2, g.ns2, g.tw2, nb);
-        tile_twiddle<true>(res, M2, nb, (uint32_t)r0, g.twM, g.twB);
+        float2 *res = tile_fft<true>(bufA, bufB, M2, g.st2, g.ns2, g.tw2, nb, (uint32_t)r0, g.twM, g.twB);
         tile_store_rows(res, ws.W, M2, r0, nb);
     }
     __threadfence_block();
     __syncthreads();
     // pass 2: column tiles + epilogue
     if (pf_d) prefetch_col_tile(pf_d, pf_N, pf_prefix, M1, M2, 0, g.real);
-    for (int c0 = 0; c0 < M2; c0 += 32) {
-        int nb = min(32, M2 - c0);
-        if (pf_d) prefetch_col_tile(pf_d, pf_N, pf_prefix, M1, M2, c0 + 32, g.real);
+    for (int c0 = 0; c0 < M2; c0 += FFT_LANES) {
+        int nb = min(FFT_LANES, M2 - c0);
+        if (pf_d) prefetch_col_tile(pf_d, pf_N, pf_prefix, M1, M2, c0 + FFT_LANES, g.real);
         tile_load_cols(bufA, ws.W, M1, M2, c0, nb);
         float2 *res = tile_fft<true>(bufA, bufB, M1, g.st1, g.ns1, g.tw1, nb);
         if (lane < nb) {

@@ -218,7 +218,7 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
             uint32_t mask = 0, jump = 0;
             for (int it = 1; it <= FFT_SCHED; it++) {
                 uint32_t c = min(mf + jump, K);
-                if (fft_cut_splits_tie(S, c, K) || (c == K && tie_cut && mf + jump == K)) mask |= 1u << (it - 1);
+                if (fft_cut_splits_tie_list(list, c, K) || (c == K && tie_cut && mf + jump == K)) mask |= 1u << (it - 1);
                 jump += it <= 17 ? hstep : tstep;
                 if (!bounded || mf + jump > K) break;
             }
@@ -346,7 +346,7 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
     }
 }
 
-__global__ void __launch_bounds__(BLOCK) k_fft(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
+__global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
                                                double max_err, const FftGeom *__restrict__ geoms, SlotPool pool,
                                                FftEntry *arena, unsigned *q) {
     extern __shared__ float2 dyn_f2[];
@@ -923,7 +923,7 @@ __device__ uint32_t dec_fft(const uint8_t *__restrict__ p, uint32_t len, uint32_
     return 0;
 }
 
-__global__ void __launch_bounds__(BLOCK) k_decode(const DecFrame *__restrict__ fr, uint32_t n,
+__global__ void __launch_bounds__(FFT_THREADS, 2) k_decode(const DecFrame *__restrict__ fr, uint32_t n,
                                                   const uint8_t *__restrict__ payloads, double *out,
                                                   const FftGeom *__restrict__ geoms, SlotPool pool,
                                                   const double *__restrict__ inv_d2, uint32_t *status, unsigned *q) {
@@ -1007,7 +1007,7 @@ void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err
 }
 void launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
                 SlotPool pool, FftEntry *arena, unsigned *q, cudaStream_t st) {
-    k_fft<<<grid_for(n, pool.fft_slots), BLOCK, FFT_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool, arena, q);
+    k_fft<<<grid_for(n, pool.fft_slots), FFT_THREADS, FFT_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool, arena, q);
 }
 void launch_noop_size(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st) {
     k_noop_size<<<grid_for(n, 2 * sms()), BLOCK, 0, st>>>(fr, n, samples, q);
@@ -1025,7 +1025,7 @@ void launch_emit(FrameWork *fr, uint32_t n, const double *samples, const FftGeom
 void launch_decode(const DecFrame *fr, uint32_t n, const uint8_t *payloads, double *out, const FftGeom *geoms,
                    SlotPool pool, const double *inv_d2, uint32_t *status, unsigned *q, cudaStream_t st) {
     int slots = pool.fft_slots < pool.dec_slots ? pool.fft_slots : pool.dec_slots;
-    k_decode<<<grid_for(n, slots), BLOCK, FFT_SMEM_BYTES, st>>>(fr, n, payloads, out, geoms, pool, inv_d2, status, q);
+    k_decode<<<grid_for(n, slots), FFT_THREADS, FFT_SMEM_BYTES, st>>>(fr, n, payloads, out, geoms, pool, inv_d2, status, q);
 }
 void launch_inv_d2(double *inv_d2, uint32_t n, cudaStream_t st) { k_inv_d2<<<(n + 255) / 256, 256, 0, st>>>(inv_d2, n); }
 

@@ -156,7 +156,7 @@ def run_reference(args):
         "impl": "reference", "metric": "auto_compress_msamples_per_s", "value": v, "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
-        "config": workload_config(n, 1),
+        "config": workload_config(args.series, args.gpus),
         "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -223,12 +223,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # page-locked result buffer: payload bytes land in it straight from the device
+    pcap = 64 << 20
+    pptr = L.atsc_gpu_host_alloc(pcap)
+    pbuf = np.ctypeslib.as_array(C.cast(pptr, C.POINTER(C.c_uint8)), shape=(pcap,))
+
     def step_dev():
         return ctx.compress_frames(None, offs, lens, atsc_b200.AUTO, ERROR_PCT / 100.0, SPEED, True,
-                                   samples_ptr=dev.data_ptr())
+                                   samples_ptr=dev.data_ptr(), payload_out=pbuf)
 
     def step_host():
-        return ctx.compress_frames(host.reshape(-1), offs, lens, atsc_b200.AUTO, ERROR_PCT / 100.0, SPEED, True)
+        return ctx.compress_frames(host.reshape(-1), offs, lens, atsc_b200.AUTO, ERROR_PCT / 100.0, SPEED, True,
+                                   payload_out=pbuf)
 
     def timed(fn, steps):
         barrier()
@@ -324,6 +330,7 @@ def main():
         }
         print(json.dumps(line))
     L.atsc_gpu_host_free(hptr)
+    L.atsc_gpu_host_free(pptr)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
