@@ -282,10 +282,8 @@ int device_init(Device &D) {
     CK(cudaMalloc((void **)&P.fft_cD, fs * FFT_DEC_KCAP * sizeof(float2)));
     CK(cudaMalloc((void **)&P.fft_cM, fs * FFT_DEC_KCAP * sizeof(float2)));
     CK(cudaMalloc((void **)&P.fft_dlist, fs * FFT_DEC_KCAP * sizeof(FftEntry)));
-    CK(cudaMalloc((void **)&P.fft_w, fs * (MAX_FRAME + 8) * 8));
     P.poly_slots = 2 * sms;
     CK(cudaMalloc((void **)&P.poly_slope, (size_t)P.poly_slots * (MAX_FRAME + 8) * 8));
-    CK(cudaMalloc((void **)&P.poly_w, (size_t)P.poly_slots * (MAX_FRAME + 8) * 8));
     size_t dsl = (size_t)P.dec_slots;
     CK(cudaMalloc((void **)&P.dec_pts, dsl * (MAX_FRAME + 8) * 8));
     CK(cudaMalloc((void **)&P.dec_mark, dsl * (MAX_FRAME + 8) * 4));
@@ -305,7 +303,7 @@ void device_free(Device &D) {
     cudaSetDevice(D.id);
     SlotPool &P = D.pool;
     void *ptrs[] = {P.rle_k0, P.rle_k1, P.rle_i0, P.rle_i1, P.rle_bnd, P.fft_W, P.fft_Xd, P.fft_keys, P.fft_rank,
-                    P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.fft_w, P.poly_slope, P.poly_w, P.dec_pts, P.dec_mark,
+                    P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.poly_slope, P.dec_pts, P.dec_mark,
                     P.dec_idx, D.inv_d2, D.queues, D.d_total, D.geoms_dev, D.d_frames, D.d_samples, D.d_arena,
                     D.d_payload, D.d_dec, D.d_pay_in, D.d_out, D.d_status};
     for (void *p : ptrs)

@@ -64,7 +64,6 @@ struct FftWs {
     uint32_t *locD, *locM, *ovr;  // [FFT_DEC_KCAP]
     float2 *cD, *cM;              // [FFT_DEC_KCAP]
     FftEntry *dlist;              // [FFT_DEC_KCAP] decode-side entry list
-    double *w;                    // [MAX_FRAME + 8] 1 / sample for the MAPE terms of the refinement loop
 };
 
 __device__ inline float2 cmul(float2 a, float2 b) {

@@ -32,7 +32,6 @@ __device__ inline FftWs fft_slot(const SlotPool &p, int s) {
     w.cD = p.fft_cD + (size_t)s * FFT_DEC_KCAP;
     w.cM = p.fft_cM + (size_t)s * FFT_DEC_KCAP;
     w.dlist = p.fft_dlist + (size_t)s * FFT_DEC_KCAP;
-    w.w = p.fft_w + (size_t)s * (MAX_FRAME + 8);
     return w;
 }
 
@@ -101,7 +100,6 @@ __global__ void __launch_bounds__(BLOCK) k_poly(FrameWork *fr, uint32_t n, const
     __shared__ int s_item;
     PolyWs ws;
     ws.slope = pool.poly_slope + (size_t)blockIdx.x * (MAX_FRAME + 8);
-    ws.w = pool.poly_w + (size_t)blockIdx.x * (MAX_FRAME + 8);
     for (;;) {
         int i = queue_next(q, &s_item);
         if (i >= (int)n) break;
@@ -202,6 +200,31 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
         __syncthreads();
     }
     const bool alias = Bn > 65536u;
+    // a later candidate can only lose to FFT on size; FFT wins ties (frame/mod.rs:77,104,141)
+    uint32_t bound = 0xFFFFFFFFu;
+    if (bounded && fw->comp == C_AUTO && fw->forced == 0xFF) {
+        if (fw->poly_valid == 1 && fw->poly_err <= max_err) bound = min(bound, fw->poly_size);
+        if (fw->rle_valid == 1) bound = min(bound, fw->rle_size);
+    }
+    if (bound != 0xFFFFFFFFu) {
+        // Early exit before any sorting: the first schedule point keeps c1 = min(max_freq, #nonzero
+        // bins) entries (fft.rs:249-252 stops at an exact zero) and the payload only grows from
+        // there.  At most `smax` of them can have a one-byte position (pos < 251 after the u16 wrap).
+        const uint32_t nz = fft_count_nonzero(Bn, ws, sh);
+        const uint32_t c1 = min(min(mf, nz), min(fw->fft_list_cap, (uint32_t)FFT_KCAP));
+        const uint32_t smax = alias ? 502u : 251u;
+        if (fft_payload_size(c1, min(c1, smax)) > bound) {
+            if (t == 0) {
+                fw->fft_count = c1;
+                fw->fft_err = max_err + 1.0;
+                fw->fft_size = 0;
+                fw->fft_iters = 1;
+                fw->fft_tie = 0;
+                fw->fft_valid = 2;
+            }
+            return;
+        }
+    }
     bool tie_cut;
     unsigned long long *S = (unsigned long long *)sm;
     const uint32_t pM = (gi >= 0 && sg->real) ? sg->M : 0u, pM1 = gi >= 0 ? sg->M1 : 1u, pM2 = gi >= 0 ? sg->M2 : 1u;
@@ -256,16 +279,8 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
         return;
     }
 
-    // a later candidate can only lose to FFT on size; FFT wins ties (frame/mod.rs:77,104,141)
-    uint32_t bound = 0xFFFFFFFFu;
-    if (fw->comp == C_AUTO && fw->forced == 0xFF) {
-        if (fw->poly_valid == 1 && fw->poly_err <= max_err) bound = min(bound, fw->poly_size);
-        if (fw->rle_valid == 1) bound = min(bound, fw->rle_size);
-    }
-
     const float Lf = (float)L;
     const double Ld = (double)L;
-    bool have_w = false;
     auto evaluate = [&](uint32_t c) -> double {
         double acc = 0.0;
         auto epi = [&](uint32_t j, float v) {
@@ -273,16 +288,7 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
             if (ix >= N) ix = N - 1;
             const double o = d[ix];
             double out = fft_round_fast(__fdiv_rn(v, Lf), o, vminf, vmaxf);
-            // reciprocal for the MAPE term (utils/error.rs:110-113): computed by the first
-            // evaluation, reused by the (up to 22) later ones
-            double w;
-            if (have_w) {
-                w = ws.w[ix];
-            } else {
-                w = __ddiv_rn(1.0, o);
-                ws.w[ix] = w;
-            }
-            acc += mape_term(out, o, w);
+            acc += mape_term(out, o);
         };
         if (gi >= 0) {
             fft_inverse(*sg, ws, c, sm, epi, d, N, prefix);
@@ -304,7 +310,6 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
             }
         }
         double s = block_sum(acc, shd);
-        have_w = true;
         return __ddiv_rn(s, Ld);
     };
 

@@ -19,10 +19,9 @@ struct SlotPool {
     float2 *fft_W, *fft_Xd, *fft_cD, *fft_cM;
     uint32_t *fft_keys, *fft_rank, *fft_locD, *fft_locM, *fft_ovr;
     FftEntry *fft_dlist;
-    double *fft_w;
     int fft_slots;
     // polynomial refinement loop (poly.cuh)
-    double *poly_slope, *poly_w;  // [MAX_FRAME + 8] per slot
+    double *poly_slope;  // [MAX_FRAME + 8] per slot
     int poly_slots;
     // decode scratch
     double *dec_pts;     // [MAX_FRAME + 8] per slot: decoded polynomial points / RLE values

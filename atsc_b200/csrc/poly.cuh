@@ -90,8 +90,7 @@ __device__ inline double idw_eval_at(const PolyKeys &k, uint32_t x, PtsFn pts,
 
 // per-CTA-slot scratch of the refinement loop
 struct PolyWs {
-    double *slope;  // [MAX_FRAME + 8] central-difference slope at every key of the current step
-    double *w;      // [MAX_FRAME]     1 / sample, computed once per frame
+    double *slope;  // [MAX_FRAME + 8] tangent (central-difference slope * step) at every key of the current step
 };
 constexpr int POLY_TAB = 136;  // step <= 133 (polynomial.rs:290 with >= max(3, N/100) points)
 struct PolyTab {
@@ -100,19 +99,28 @@ struct PolyTab {
     double h00[POLY_TAB], h10[POLY_TAB], h01[POLY_TAB], h11[POLY_TAB];  // cubic Hermite basis at t
 };
 
-// One MAPE term |(out - o) / o| (utils/error.rs:110-113) through the precomputed reciprocal
-// w = 1/o: deviates from the true division by <= 1 ulp (absorbed by the near-tie tolerance, the
-// error only feeds threshold tests) while exact zeros stay exactly zero.  A zero sample keeps the
+// f64::round (half away from zero) without the library call: trunc + exact remainder test
+__device__ inline double round_half_away(double y) {
+    double r = trunc(y);
+    double diff = __dsub_rn(y, r);  // exact
+    if (fabs(diff) >= 0.5) r = __dadd_rn(r, copysign(1.0, y));
+    return r;
+}
+
+// One MAPE term |(out - o) / o| (utils/error.rs:110-113) through the reciprocal w = 1/o (IEEE):
+// deviates from the true division by <= 1 ulp (absorbed by the near-tie tolerance, the error only
+// feeds threshold tests) while exact zeros stay exactly zero.  A zero sample keeps the
 // reference's semantics: w = inf gives |out * inf - 1| = inf (out != 0) or NaN (out == 0), SURVEY H5.
 __device__ inline double mape_term(double out, double o, double w) {
     return (out == o && o != 0.0) ? 0.0 : fabs(fma(out, w, -1.0));
 }
+__device__ inline double mape_term(double out, double o) { return mape_term(out, o, __drcp_rn(o)); }
 // (x * 1e5).round() / 1e5 for the error loops.  `* 1e-5` replaces the true division (<= 1 ulp off)
 // unless the result lands within 2 ulp of the original sample `o`: an exactly reproduced sample
 // must give an exactly zero error term (lossless `-e 0` relies on `error <= 0`), so that case
 // takes the IEEE quotient.  Only the decompressor always needs the exact quotient.
 __device__ inline double round5_loop(double x, double o) {
-    double n = round(__dmul_rn(x, 100000.0));
+    double n = round_half_away(__dmul_rn(x, 100000.0));
     double out = n * 1e-5;
     if (fabs(out - o) <= fabs(o) * 4.5e-16) out = __ddiv_rn(n, 100000.0);
     return out;
@@ -127,10 +135,11 @@ __device__ inline double round_and_limit5_fast(double x, double o, double mn, do
 // MAPE (utils/error.rs:104-116) of one candidate step against the frame; block-wide.
 // Catmull-Rom path: identical value arithmetic to poly_eval_at (same operations, same order),
 // but everything that depends only on the offset inside a segment comes from a table and the
-// per-key tangents from a pre-pass, so the inner loop has no division.
+// per-key tangents from a pre-pass, so the inner loop has no division besides the reciprocal
+// of the sample.
 __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys &k, int ptype,
                                    double vmin, double vmax, const double *__restrict__ inv_d2,
-                                   PolyWs ws, PolyTab *tab, bool have_w, double *scratch) {
+                                   PolyWs ws, PolyTab *tab, double *scratch) {
     const uint32_t N = k.N, step = k.step, K = k.K, T = blockDim.x, t = threadIdx.x;
     double acc = 0.0;
     auto pts = [&](uint32_t j) { return d[poly_pos(k, j)]; };
@@ -139,9 +148,7 @@ __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys 
             double v = ptype ? idw_eval_at(k, x, pts, inv_d2) : poly_eval_at(k, x, pts);
             double o = d[x];
             double out = round_and_limit5_fast(v, o, vmin, vmax);
-            double w = have_w ? ws.w[x] : __ddiv_rn(1.0, o);
-            if (!have_w) ws.w[x] = w;
-            acc += mape_term(out, o, w);
+            acc += mape_term(out, o);
         }
         double s = block_sum(acc, scratch);
         return __ddiv_rn(s, (double)N);
@@ -160,24 +167,30 @@ __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys 
         tab->h01[j] = __dsub_rn(three_t2, two_t3);
         tab->h11[j] = __dsub_rn(t3, t2);
     }
-    // ---- central-difference slope at every interior key: (v[j+1] - v[j-1]) / (pos[j+1] - pos[j-1])
+    // ---- tangent at every interior key: (v[j+1] - v[j-1]) / (pos[j+1] - pos[j-1]) * step
+    // (both segments that use it as a Catmull-Rom tangent are regular, i.e. `step` long)
+    double *__restrict__ tang = ws.slope;
     for (uint32_t j = 1 + t; j + 1 < K; j += T) {
         uint32_t pa = poly_pos(k, j - 1), pb = poly_pos(k, j + 1);
-        ws.slope[j] = __ddiv_rn(__dsub_rn(d[pb], d[pa]), __dsub_rn((double)pb, (double)pa));
+        tang[j] = __dmul_rn(__ddiv_rn(__dsub_rn(d[pb], d[pa]), __dsub_rn((double)pb, (double)pa)), stepd);
     }
     __syncthreads();
     const uint32_t Kreg = k.Kreg;
     const uint32_t last_reg = (Kreg - 1) * step;  // position of the last regular key
-    // (i, j) = (x / step, x % step) advanced incrementally
-    uint32_t i = t / step, j = t - i * step;
-    const uint32_t di = T / step, dj = T - di * step;
-    for (uint32_t x = t; x < N; x += T, i += di, j += dj) {
-        if (j >= step) {
-            j -= step;
-            i++;
-        }
+    const uint32_t magic = (uint32_t)((0x100000000ull + step - 1) / step);  // x / step == umulhi(x, magic), x < 2^17
+#pragma unroll 4
+    for (uint32_t x = t; x < N; x += T) {
+        const uint32_t i = __umulhi(x, magic), j = x - i * step;
         double v;
-        if (x == N - 1) {
+        if (i >= 1 && i + 2 < K) {
+            // regular Catmull-Rom segment (polynomial.rs:349: key i is CatmullRom iff 0 < i < K-2)
+            const double av = d[i * step], bv = d[(i + 1) * step];
+            double c0 = __dmul_rn(av, tab->h00[j]);
+            double c1 = __dmul_rn(tang[i], tab->h10[j]);
+            double c2 = __dmul_rn(bv, tab->h01[j]);
+            double c3 = __dmul_rn(tang[i + 1], tab->h11[j]);
+            v = __dadd_rn(__dadd_rn(__dadd_rn(c0, c1), c2), c3);
+        } else if (x == N - 1) {
             v = d[N - 1];
         } else if (i == Kreg - 1) {
             // irregular last segment [last_reg, N-1]: always Linear (it is segment K-2)
@@ -185,27 +198,13 @@ __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys 
             double nt = __ddiv_rn(__dsub_rn((double)x, at), __dsub_rn(bt, at));
             v = __dadd_rn(__dmul_rn(d[last_reg], __dsub_rn(1.0, nt)), __dmul_rn(d[N - 1], nt));
         } else {
-            const double av = d[i * step];
-            const uint32_t pb = (i + 1 < Kreg) ? (i + 1) * step : N - 1;  // == (i+1)*step here
-            const double bv = d[pb];
-            const bool catmull = (i > 0) && (K - i > 2);
-            if (!catmull) {
-                v = __dadd_rn(__dmul_rn(av, tab->lin0[j]), __dmul_rn(bv, tab->tt[j]));
-            } else {
-                double m0 = __dmul_rn(ws.slope[i], stepd);
-                double m1 = __dmul_rn(ws.slope[i + 1], stepd);
-                double c0 = __dmul_rn(av, tab->h00[j]);
-                double c1 = __dmul_rn(m0, tab->h10[j]);
-                double c2 = __dmul_rn(bv, tab->h01[j]);
-                double c3 = __dmul_rn(m1, tab->h11[j]);
-                v = __dadd_rn(__dadd_rn(__dadd_rn(c0, c1), c2), c3);
-            }
+            // first segment, or the regular segment K-2: Linear
+            const uint32_t pb = (i + 1 < Kreg) ? (i + 1) * step : N - 1;
+            v = __dadd_rn(__dmul_rn(d[i * step], tab->lin0[j]), __dmul_rn(d[pb], tab->tt[j]));
         }
-        double o = d[x];
-        double out = round_and_limit5_fast(v, o, vmin, vmax);
-        double w = have_w ? ws.w[x] : __ddiv_rn(1.0, o);
-        if (!have_w) ws.w[x] = w;
-        acc += mape_term(out, o, w);
+        const double o = d[x];
+        const double out = round_and_limit5_fast(v, o, vmin, vmax);
+        acc += mape_term(out, o);
     }
     double s = block_sum(acc, scratch);
     return __ddiv_rn(s, (double)N);
@@ -262,7 +261,6 @@ __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, d
             const double target = round_f64_dec(max_err, 3);
             uint32_t prev_step = 0;
             double prev_err = 0.0;
-            bool have_w = false;
             while (target < round_f64_dec(cur, 4)) {
                 it++;
                 uint32_t points = baseline + jump;
@@ -274,8 +272,7 @@ __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, d
                 } else if (step == 1 && it <= 22) {
                     cur = 0.0;  // value unused: the `len == data_len` exit below overrides it
                 } else {
-                    cur = poly_mape(d, k, ptype, vmin, vmax, inv_d2, ws, tab, have_w, sh);
-                    have_w = true;
+                    cur = poly_mape(d, k, ptype, vmin, vmax, inv_d2, ws, tab, sh);
                 }
                 prev_step = step;
                 prev_err = cur;
