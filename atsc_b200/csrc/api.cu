@@ -46,6 +46,9 @@ struct Device {
     size_t samples_cap = 0;
     FftEntry *d_arena = nullptr;
     size_t arena_cap = 0;
+    float2 *d_spec_xd = nullptr;  // per-frame half spectra of the wave (k_fft_fwd -> k_fft)
+    uint32_t *d_spec_keys = nullptr;
+    size_t spec_xd_cap = 0, spec_keys_cap = 0;
     uint8_t *d_payload = nullptr, *h_payload = nullptr;
     size_t payload_cap = 0, h_payload_cap = 0;
     DecFrame *d_dec = nullptr, *h_dec = nullptr;
@@ -187,6 +190,14 @@ int get_geom(Device &D, uint32_t L, int *out_idx) {
             b2 = m2;
         }
     }
+    // lengths 2^a 3^7 (every power-of-two frame of 8192..131072 samples): M1 x 243, the split the
+    // register-radix forward engine (fft2.cuh) is written for
+    const bool fast = g.real && g.M % 243 == 0 &&
+                      (g.M / 243 == 288 || g.M / 243 == 144 || g.M / 243 == 72 || g.M / 243 == 36 || g.M / 243 == 18);
+    if (fast) {
+        b1 = g.M / 243;
+        b2 = 243;
+    }
     if (!b1) return ATSC_ERR_UNSUPPORTED;
     g.M1 = b1;
     g.M2 = b2;
@@ -221,6 +232,13 @@ int get_geom(Device &D, uint32_t L, int *out_idx) {
     if ((rc = upload_vec(D, twL2, &g.twL2))) return rc;
     if ((rc = upload_vec(D, twA, &g.twA))) return rc;
     if ((rc = upload_vec(D, twB, &g.twB))) return rc;
+    g.T4 = nullptr;
+    if (fast) {
+        std::vector<float2> T4((size_t)g.M);
+        for (uint32_t n2 = 0; n2 < g.M2; n2++)
+            for (uint32_t k1 = 0; k1 < g.M1; k1++) T4[(size_t)n2 * g.M1 + k1] = root((double)(((uint64_t)k1 * n2) % g.M), g.M);
+        if ((rc = upload_vec(D, T4, &g.T4))) return rc;
+    }
     int idx = (int)D.geoms_host.size();
     D.geoms_host.push_back(g);
     D.geom_idx[L] = idx;
@@ -305,7 +323,7 @@ void device_free(Device &D) {
     void *ptrs[] = {P.rle_k0, P.rle_k1, P.rle_i0, P.rle_i1, P.rle_bnd, P.fft_W, P.fft_Xd, P.fft_keys, P.fft_rank,
                     P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.poly_slope, P.dec_pts, P.dec_mark,
                     P.dec_idx, D.inv_d2, D.queues, D.d_total, D.geoms_dev, D.d_frames, D.d_samples, D.d_arena,
-                    D.d_payload, D.d_dec, D.d_pay_in, D.d_out, D.d_status};
+                    D.d_payload, D.d_dec, D.d_pay_in, D.d_out, D.d_status, D.d_spec_xd, D.d_spec_keys};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (void *p : D.geom_allocs) cudaFree(p);
@@ -346,7 +364,7 @@ int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &re
     size_t hcap = D.frames_cap;
     if ((rc = grow(D, D.d_frames, D.frames_cap, n))) return rc;
     if ((rc = grow(D, D.h_frames, hcap, D.frames_cap, true))) return rc;
-    uint64_t arena = 0;
+    uint64_t arena = 0, spec = 0;
     bool any_noop = false;
     for (uint32_t i = 0; i < n; i++) {
         FrameWork &f = D.h_frames[i];
@@ -359,6 +377,7 @@ int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &re
         f.select_only = r.select_only;
         f.forced = r.forced;
         f.geom = -1;
+        f.spec_off = ~0ull;
         uint8_t eff = (r.comp == C_AUTO && r.forced != 0xFF) ? r.forced : r.comp;
         any_noop |= r.comp == C_NOOP;
         if (eff == C_FFT || eff == C_AUTO) {
@@ -370,6 +389,10 @@ int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &re
                     return rc;
                 }
                 f.geom = gi;
+                if (D.geoms_host[gi].T4) {
+                    f.spec_off = spec;
+                    spec += D.geoms_host[gi].M + 8;
+                }
             }
             uint32_t mf = std::max<uint32_t>(3, r.len / 100);
             uint32_t kmax = r.bounded ? mf + 17 * std::max<uint32_t>(mf / 2, 1) + 5 * std::max<uint32_t>(mf / 10, 1) : mf;
@@ -381,6 +404,8 @@ int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &re
     }
     if ((rc = sync_geoms(D))) return rc;
     if ((rc = grow(D, D.d_arena, D.arena_cap, (size_t)arena + 1))) return rc;
+    if ((rc = grow(D, D.d_spec_xd, D.spec_xd_cap, (size_t)spec + 1))) return rc;
+    if ((rc = grow(D, D.d_spec_keys, D.spec_keys_cap, (size_t)spec + 1))) return rc;
     CK(cudaMemcpyAsync(D.d_frames, D.h_frames, (size_t)n * sizeof(FrameWork), cudaMemcpyHostToDevice, D.st));
     CK(cudaMemsetAsync(D.queues, 0, 64 * sizeof(unsigned), D.st));
     CK(cudaEventRecord(D.ev[0], D.st));
@@ -391,7 +416,11 @@ int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &re
     CK(cudaEventRecord(D.ev[2], D.st));
     launch_rle(D.d_frames, n, d_samples, max_err, D.pool, D.queues + 2, D.st);
     CK(cudaEventRecord(D.ev[3], D.st));
-    launch_fft(D.d_frames, n, d_samples, max_err, D.geoms_dev, D.pool, D.d_arena, D.queues + 3, D.st);
+    if (spec) {
+        launch_fft_fwd(D.d_frames, n, d_samples, max_err, D.geoms_dev, D.pool, D.d_spec_xd, D.d_spec_keys, D.queues + 7, D.st);
+        D.launches++;
+    }
+    launch_fft(D.d_frames, n, d_samples, max_err, D.geoms_dev, D.pool, D.d_arena, D.d_spec_xd, D.d_spec_keys, D.queues + 3, D.st);
     CK(cudaEventRecord(D.ev[4], D.st));
     D.launches += 5;
     if (any_noop) {

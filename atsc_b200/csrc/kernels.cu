@@ -5,6 +5,7 @@
 // Pipeline per wave (compress):  stats -> plan -> poly -> rle -> fft -> select -> scan -> emit
 // Reference citations are relative to /root/reference/atsc/src/.
 #include "kernels.h"
+#include "fft2.cuh"
 #include "poly.cuh"
 #include "stats.cuh"
 #include "varscan.cuh"
@@ -38,7 +39,7 @@ __device__ inline FftWs fft_slot(const SlotPool &p, int s) {
 // =========================================================================================
 // stats
 // =========================================================================================
-__global__ void __launch_bounds__(BLOCK) k_stats(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
+__global__ void __launch_bounds__(BLOCK, 2) k_stats(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
                                                  unsigned *q) {
     __shared__ StatsSmem sm;
     __shared__ int s_item;
@@ -87,6 +88,7 @@ __global__ void k_plan(FrameWork *fr, uint32_t n) {
     fw->poly_iters = fw->fft_iters = 0;
     fw->fft_count = 0;
     fw->aux_size = 0;
+    fw->fwd_done = 0;
 }
 
 // =========================================================================================
@@ -150,7 +152,8 @@ __device__ inline bool fft_loop_near_tie(double cur, int E) {
 }
 
 __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const FftGeom *__restrict__ geoms,
-                          FftWs ws, FftEntry *list, double max_err, float2 *sm, double *shd, FftGeom *sg) {
+                          FftWs ws, FftEntry *list, double max_err, float2 *sm, double *shd, FftGeom *sg,
+                          float2 *spec_xd, uint32_t *spec_keys) {
     uint32_t *sh = (uint32_t *)shd;
     const uint32_t N = fw->len;
     const bool bounded = fw->bounded != 0;
@@ -180,7 +183,13 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
         L = sg->L;
         Bn = sg->Bn;
         if (bounded && N >= 128) prefix = (L - N) / 2;
-        fft_forward(d, N, prefix, *sg, ws, sm);
+        if (fw->fwd_done) {
+            // k_fft_fwd (fft2.cuh) already produced the half spectrum and its keys
+            ws.Xd = spec_xd + fw->spec_off;
+            ws.keys = spec_keys + fw->spec_off;
+        } else {
+            fft_forward(d, N, prefix, *sg, ws, sm);
+        }
     } else {
         // direct DFT, no padding
         L = N;
@@ -206,7 +215,7 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
         if (fw->poly_valid == 1 && fw->poly_err <= max_err) bound = min(bound, fw->poly_size);
         if (fw->rle_valid == 1) bound = min(bound, fw->rle_size);
     }
-    if (bound != 0xFFFFFFFFu) {
+    if (bound != 0xFFFFFFFFu && !fw->fwd_done) {
         // Early exit before any sorting: the first schedule point keeps c1 = min(max_freq, #nonzero
         // bins) entries (fft.rs:249-252 stops at an exact zero) and the payload only grows from
         // there.  At most `smax` of them can have a one-byte position (pos < 251 after the u16 wrap).
@@ -353,7 +362,7 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
 
 __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
                                                double max_err, const FftGeom *__restrict__ geoms, SlotPool pool,
-                                               FftEntry *arena, unsigned *q) {
+                                               FftEntry *arena, float2 *spec_xd, uint32_t *spec_keys, unsigned *q) {
     extern __shared__ float2 dyn_f2[];
     __shared__ double shd[64];
     __shared__ FftGeom sg;
@@ -363,8 +372,65 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FrameWork *fr, uint32_t 
         int i = queue_next(q, &s_item);
         if (i >= (int)n) break;
         FrameWork *fw = &fr[i];
-        if (!fw->need_fft) continue;
-        fft_frame(samples + fw->off, fw, geoms, ws, arena + fw->fft_list_off, max_err, dyn_f2, shd, &sg);
+        if (!fw->need_fft || fw->fft_valid == 2) continue;  // 2: k_fft_fwd proved the candidate cannot win
+        fft_frame(samples + fw->off, fw, geoms, ws, arena + fw->fft_list_off, max_err, dyn_f2, shd, &sg, spec_xd,
+                  spec_keys);
+    }
+}
+
+// forward transform (fft2.cuh) of every eligible frame, ahead of k_fft.  Auto frames whose first
+// schedule point is already larger than a passing Polynomial / RLE payload end here (fft_valid = 2)
+// without ever storing a spectrum; everything else leaves Xd / keys in the wave's spectrum arena.
+__global__ void __launch_bounds__(F2_THREADS, 2) k_fft_fwd(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
+                                                           double max_err, const FftGeom *__restrict__ geoms,
+                                                           SlotPool pool, float2 *spec_xd, uint32_t *spec_keys,
+                                                           unsigned *q) {
+    extern __shared__ float2 dyn_f2[];
+    __shared__ uint32_t sh[40];
+    __shared__ FftGeom sg;
+    __shared__ int s_item;
+    float2 *W = pool.fft_W + (size_t)blockIdx.x * MAX_FFT_LEN;
+    const uint32_t t = threadIdx.x;
+    for (;;) {
+        int i = queue_next(q, &s_item);
+        if (i >= (int)n) break;
+        FrameWork *fw = &fr[i];
+        if (!fw->need_fft || fw->f32_const || fw->geom < 0 || fw->spec_off == ~0ull) continue;
+        if (t == 0) sg = geoms[fw->geom];
+        __syncthreads();
+        const uint32_t N = fw->len;
+        const bool bounded = fw->bounded != 0;
+        const uint32_t prefix = (bounded && N >= 128) ? (sg.L - N) / 2 : 0u;
+        f2_forward_pass1(samples + fw->off, (int)N, (int)prefix, sg, W, dyn_f2);
+        float2 *Xd = spec_xd + fw->spec_off;
+        uint32_t *keys = spec_keys + fw->spec_off;
+        // a later candidate can only lose to FFT on size; FFT wins ties (frame/mod.rs:77,104,141)
+        uint32_t bound = 0xFFFFFFFFu;
+        if (bounded && fw->comp == C_AUTO && fw->forced == 0xFF) {
+            if (fw->poly_valid == 1 && fw->poly_err <= max_err) bound = min(bound, fw->poly_size);
+            if (fw->rle_valid == 1) bound = min(bound, fw->rle_size);
+        }
+        if (bound != 0xFFFFFFFFu) {
+            // count-only second pass: the first schedule point keeps c1 = min(max_freq, #nonzero bins)
+            // entries (fft.rs:249-252) and at most `smax` of them have a one-byte position
+            const uint32_t nz = block_sum_u32(f2_pass2<false>((int)sg.M1, sg.tw2, sg.twL1, sg.twL2, W, dyn_f2, Xd, keys), sh);
+            const uint32_t mf = (3 >= N / 100) ? 3 : N / 100;
+            const uint32_t c1 = min(min(mf, nz), min(fw->fft_list_cap, (uint32_t)FFT_KCAP));
+            const uint32_t smax = sg.Bn > 65536u ? 502u : 251u;
+            if (fft_payload_size(c1, min(c1, smax)) > bound) {
+                if (t == 0) {
+                    fw->fft_count = c1;
+                    fw->fft_err = max_err + 1.0;
+                    fw->fft_size = 0;
+                    fw->fft_iters = 1;
+                    fw->fft_tie = 0;
+                    fw->fft_valid = 2;
+                }
+                continue;
+            }
+        }
+        (void)f2_pass2<true>((int)sg.M1, sg.tw2, sg.twL1, sg.twL2, W, dyn_f2, Xd, keys);
+        if (t == 0) fw->fwd_done = 1;
     }
 }
 
@@ -990,6 +1056,8 @@ int kernels_init() {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fft_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_rle, cudaFuncAttributeMaxDynamicSharedMemorySize, RLE_HIST_WORDS * 4);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, RLE_HIST_WORDS * 4);
@@ -1011,8 +1079,14 @@ void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err
     k_rle<<<grid_for(n, pool.rle_slots), BLOCK, RLE_HIST_WORDS * 4, st>>>(fr, n, samples, max_err, pool, q);
 }
 void launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
-                SlotPool pool, FftEntry *arena, unsigned *q, cudaStream_t st) {
-    k_fft<<<grid_for(n, pool.fft_slots), FFT_THREADS, FFT_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool, arena, q);
+                SlotPool pool, FftEntry *arena, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st) {
+    k_fft<<<grid_for(n, pool.fft_slots), FFT_THREADS, FFT_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool, arena,
+                                                                           spec_xd, spec_keys, q);
+}
+void launch_fft_fwd(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
+                    SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st) {
+    k_fft_fwd<<<grid_for(n, pool.fft_slots), F2_THREADS, F2_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool,
+                                                                             spec_xd, spec_keys, q);
 }
 void launch_noop_size(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st) {
     k_noop_size<<<grid_for(n, 2 * sms()), BLOCK, 0, st>>>(fr, n, samples, q);

@@ -48,7 +48,9 @@ void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_er
 void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err, SlotPool pool,
                 unsigned *q, cudaStream_t st);
 void launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
-                SlotPool pool, FftEntry *arena, unsigned *q, cudaStream_t st);
+                SlotPool pool, FftEntry *arena, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st);
+void launch_fft_fwd(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
+                    SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st);
 void launch_noop_size(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st);
 void launch_select(FrameWork *fr, uint32_t n, double max_err, cudaStream_t st);
 void launch_scan(FrameWork *fr, uint32_t n, unsigned long long *total, cudaStream_t st);

@@ -178,33 +178,40 @@ __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys 
     const uint32_t Kreg = k.Kreg;
     const uint32_t last_reg = (Kreg - 1) * step;  // position of the last regular key
     const uint32_t magic = (uint32_t)((0x100000000ull + step - 1) / step);  // x / step == umulhi(x, magic), x < 2^17
-#pragma unroll 4
-    for (uint32_t x = t; x < N; x += T) {
-        const uint32_t i = __umulhi(x, magic), j = x - i * step;
-        double v;
-        if (i >= 1 && i + 2 < K) {
-            // regular Catmull-Rom segment (polynomial.rs:349: key i is CatmullRom iff 0 < i < K-2)
-            const double av = d[i * step], bv = d[(i + 1) * step];
-            double c0 = __dmul_rn(av, tab->h00[j]);
-            double c1 = __dmul_rn(tang[i], tab->h10[j]);
-            double c2 = __dmul_rn(bv, tab->h01[j]);
-            double c3 = __dmul_rn(tang[i + 1], tab->h11[j]);
-            v = __dadd_rn(__dadd_rn(__dadd_rn(c0, c1), c2), c3);
-        } else if (x == N - 1) {
-            v = d[N - 1];
-        } else if (i == Kreg - 1) {
-            // irregular last segment [last_reg, N-1]: always Linear (it is segment K-2)
-            double at = (double)last_reg, bt = (double)(N - 1);
-            double nt = __ddiv_rn(__dsub_rn((double)x, at), __dsub_rn(bt, at));
-            v = __dadd_rn(__dmul_rn(d[last_reg], __dsub_rn(1.0, nt)), __dmul_rn(d[N - 1], nt));
-        } else {
-            // first segment, or the regular segment K-2: Linear
-            const uint32_t pb = (i + 1 < Kreg) ? (i + 1) * step : N - 1;
-            v = __dadd_rn(__dmul_rn(d[i * step], tab->lin0[j]), __dmul_rn(d[pb], tab->tt[j]));
+    constexpr int U = 4;  // samples in flight per thread: their loads are issued before any arithmetic
+    for (uint32_t x0 = t; x0 < N; x0 += U * T) {
+        double o[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) o[u] = (x0 + u * T < N) ? d[x0 + u * T] : 1.0;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t x = x0 + u * T;
+            if (x >= N) break;
+            const uint32_t i = __umulhi(x, magic), j = x - i * step;
+            double v;
+            if (i >= 1 && i + 2 < K) {
+                // regular Catmull-Rom segment (polynomial.rs:349: key i is CatmullRom iff 0 < i < K-2)
+                const double av = d[i * step], bv = d[(i + 1) * step];
+                double c0 = __dmul_rn(av, tab->h00[j]);
+                double c1 = __dmul_rn(tang[i], tab->h10[j]);
+                double c2 = __dmul_rn(bv, tab->h01[j]);
+                double c3 = __dmul_rn(tang[i + 1], tab->h11[j]);
+                v = __dadd_rn(__dadd_rn(__dadd_rn(c0, c1), c2), c3);
+            } else if (x == N - 1) {
+                v = d[N - 1];
+            } else if (i == Kreg - 1) {
+                // irregular last segment [last_reg, N-1]: always Linear (it is segment K-2)
+                double at = (double)last_reg, bt = (double)(N - 1);
+                double nt = __ddiv_rn(__dsub_rn((double)x, at), __dsub_rn(bt, at));
+                v = __dadd_rn(__dmul_rn(d[last_reg], __dsub_rn(1.0, nt)), __dmul_rn(d[N - 1], nt));
+            } else {
+                // first segment, or the regular segment K-2: Linear
+                const uint32_t pb = (i + 1 < Kreg) ? (i + 1) * step : N - 1;
+                v = __dadd_rn(__dmul_rn(d[i * step], tab->lin0[j]), __dmul_rn(d[pb], tab->tt[j]));
+            }
+            const double out = round_and_limit5_fast(v, o[u], vmin, vmax);
+            acc += mape_term(out, o[u]);
         }
-        const double o = d[x];
-        const double out = round_and_limit5_fast(v, o, vmin, vmax);
-        acc += mape_term(out, o);
     }
     double s = block_sum(acc, scratch);
     return __ddiv_rn(s, (double)N);

@@ -40,11 +40,11 @@ __device__ inline void frame_stats(const double *__restrict__ d, uint32_t N, Fra
                                    StatsSmem *sm) {
     const double first = d[0];
     double mn = first, mx = first;
-    uint32_t flags = 0;  // bit0 fractional, bit1 saw +0.0, bit2 saw -0.0
+    uint32_t flags = 0;  // bit0 fractional, bit1 saw -0.0
     uint32_t runs = 0, idxb = 0;
     const uint32_t T = blockDim.x;
     const int ln = threadIdx.x & 31;
-    constexpr int U = 8;  // independent coalesced loads in flight per thread
+    constexpr int U = 4;  // independent coalesced loads in flight per thread
     for (uint32_t i0 = 0; i0 < N; i0 += U * T) {
         double v[U], nx[U];
         const uint32_t base = i0 + threadIdx.x;
@@ -67,7 +67,7 @@ __device__ inline void frame_stats(const double *__restrict__ d, uint32_t N, Fra
             if (i >= N) continue;
             const double val = v[u];
             flags |= frac_nonzero(val) ? 1u : 0u;
-            if (val == 0.0) flags |= (__double2hiint(val) < 0) ? 4u : 2u;
+            if (__double_as_longlong(val) == (long long)0x8000000000000000ull) flags |= 2u;
             if (val < mn) mn = val;
             if (val > mx) mx = val;
             // rle.rs:154: run ends where the next value differs (or at the end)
@@ -111,8 +111,8 @@ __device__ inline void frame_stats(const double *__restrict__ d, uint32_t N, Fra
     double vmin = mn, vmax = mx;
     if (first != first) {
         vmin = vmax = first;  // min = max = data[0] = NaN and no comparison ever replaces it
-    } else if ((flags & 6u) == 6u && (vmin == 0.0 || vmax == 0.0)) {
-        // both zeros present and an extreme is zero: its sign is that of the first zero in the frame
+    } else if ((flags & 2u) && (vmin == 0.0 || vmax == 0.0)) {
+        // a -0.0 exists and an extreme is zero: its sign is that of the first zero in the frame
         uint32_t fz = 0xFFFFFFFFu;
         for (uint32_t x = threadIdx.x; x < N; x += T)
             if (d[x] == 0.0) {
