@@ -2,11 +2,17 @@
 //
 // There is deliberately NO CPU fallback: every entry point fails with ATSC_ERR_CUDA when no
 // CUDA device is usable.
+//
+// A call's frames are cut into waves; each wave is one asynchronous sequence
+//   [H2D samples] -> stats -> plan -> poly -> rle -> fft_fwd -> fft -> select -> scan -> emit -> D2H records
+// on the stream of one of the device's ENGINES (stream + private workspaces).  Several waves are
+// in flight at once, so one wave's copies and kernel tails overlap the next wave's kernels.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -21,25 +27,39 @@ using namespace atsc;
 
 namespace {
 
-constexpr uint64_t WAVE_SAMPLES = 48ull << 20;  // samples per wave (384 MiB of f64)
 constexpr uint32_t WAVE_FRAMES = 1u << 18;
+constexpr int MAX_ENGINES = 4;
+constexpr size_t GEOM_CAP = 512;  // distinct transform lengths 2^a 3^b <= 139968 (about 120 exist)
 
-struct Device {
-    int id = 0;
+struct FrameReq {
+    uint64_t off;
+    uint32_t len;
+    uint8_t comp, bounded, select_only, forced;
+};
+
+// device-side control words of one wave
+struct WaveCtl {
+    unsigned long long total;  // payload bytes of the wave (k_scan)
+    unsigned overflow;         // k_emit: total did not fit the payload buffer
+    unsigned pad;
+};
+
+// a wave that has been issued on an engine and not yet collected
+struct WaveJob {
+    bool active = false;
+    uint32_t pos = 0, n = 0;          // frames idx[pos .. pos+n) of the call
+    const double *d_samples = nullptr;
+    std::vector<FrameReq> reqs;
+    std::vector<uint8_t> tie1;        // sampled selection pass: its near-tie bits / diagnostics
+    std::vector<atsc_frame_out> diag1;
+    bool sampled = false, any_emit_ev = false;
+};
+
+struct Engine {
     cudaStream_t st = nullptr;
     SlotPool pool{};
-    double *inv_d2 = nullptr;
     unsigned *queues = nullptr;
-    unsigned long long *d_total = nullptr, *h_total = nullptr;
-    // geometry cache
-    std::map<uint32_t, int> geom_idx;
-    std::map<uint32_t, uint32_t> pad_cache;
-    std::vector<FftGeom> geoms_host;
-    std::vector<void *> geom_allocs;
-    FftGeom *geoms_dev = nullptr;
-    size_t geoms_dev_cap = 0;
-    bool geoms_dirty = false;
-    // growable buffers
+    WaveCtl *d_ctl = nullptr, *h_ctl = nullptr;
     FrameWork *d_frames = nullptr, *h_frames = nullptr;
     size_t frames_cap = 0;
     double *d_samples = nullptr;
@@ -49,8 +69,9 @@ struct Device {
     float2 *d_spec_xd = nullptr;  // per-frame half spectra of the wave (k_fft_fwd -> k_fft)
     uint32_t *d_spec_keys = nullptr;
     size_t spec_xd_cap = 0, spec_keys_cap = 0;
-    uint8_t *d_payload = nullptr, *h_payload = nullptr;
-    size_t payload_cap = 0, h_payload_cap = 0;
+    uint8_t *d_payload = nullptr;
+    size_t payload_cap = 0;
+    // decode
     DecFrame *d_dec = nullptr, *h_dec = nullptr;
     size_t dec_cap = 0;
     uint8_t *d_pay_in = nullptr;
@@ -59,10 +80,28 @@ struct Device {
     size_t out_cap = 0;
     uint32_t *d_status = nullptr, *h_status = nullptr;
     size_t status_cap = 0;
-    uint64_t launches = 0;
-    // CUDA-event timing of every kernel on this device's stream (ms accumulated since reset):
-    // 0 stats, 1 plan+poly, 2 rle, 3 fft, 4 noop+select+scan, 5 emit, 6 decode, 7 unused
+    // CUDA events around every kernel of the wave (kernel_ms)
     cudaEvent_t ev[10] = {};
+    WaveJob job;
+};
+
+struct Device {
+    int id = 0;
+    cudaStream_t st = nullptr;  // setup stream (tables)
+    int n_engines = 0;
+    Engine eng[MAX_ENGINES];
+    uint64_t wave_samples = 0;
+    double *inv_d2 = nullptr;
+    // geometry cache
+    std::map<uint32_t, int> geom_idx;
+    std::map<uint32_t, uint32_t> pad_cache;
+    std::vector<FftGeom> geoms_host;
+    std::vector<void *> geom_allocs;
+    FftGeom *geoms_dev = nullptr;  // GEOM_CAP entries, appended to (never reallocated: waves in flight read it)
+    size_t geoms_uploaded = 0;
+    uint64_t launches = 0;
+    // CUDA-event time of every kernel (ms accumulated since reset):
+    // 0 stats, 1 plan+poly, 2 rle, 3 fft_fwd+fft, 4 noop+select+scan, 5 emit, 6 decode, 7 unused
     double ms[8] = {};
     std::string err;
 };
@@ -87,11 +126,14 @@ namespace {
         }                                                                                          \
     } while (0)
 
+// grows a buffer that only the engine's own stream touches: the stream is drained first so no
+// kernel of an earlier wave still uses the old allocation
 template <class T>
-int grow(Device &D, T *&p, size_t &cap, size_t need, bool pinned_host = false) {
+int grow(Device &D, cudaStream_t st, T *&p, size_t &cap, size_t need, bool pinned_host = false) {
     if (need <= cap) return ATSC_OK;
     size_t nc = std::max(need, cap + cap / 2);
     if (p) {
+        CK(cudaStreamSynchronize(st));
         if (pinned_host)
             CK(cudaFreeHost(p));
         else
@@ -242,7 +284,6 @@ int get_geom(Device &D, uint32_t L, int *out_idx) {
     int idx = (int)D.geoms_host.size();
     D.geoms_host.push_back(g);
     D.geom_idx[L] = idx;
-    D.geoms_dirty = true;
     *out_idx = idx;
     return ATSC_OK;
 }
@@ -257,32 +298,28 @@ uint32_t padded_len(Device &D, uint32_t len) {
     return L;
 }
 
+// uploads geometries created since the last call (append only)
 int sync_geoms(Device &D) {
-    if (!D.geoms_dirty) return ATSC_OK;
-    int rc = grow(D, D.geoms_dev, D.geoms_dev_cap, D.geoms_host.size() + 8);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(D.geoms_dev, D.geoms_host.data(), D.geoms_host.size() * sizeof(FftGeom),
-                       cudaMemcpyHostToDevice, D.st));
+    if (D.geoms_uploaded == D.geoms_host.size()) return ATSC_OK;
+    if (D.geoms_host.size() > GEOM_CAP) {
+        D.err = "too many distinct FFT lengths";
+        return ATSC_ERR_UNSUPPORTED;
+    }
+    CK(cudaMemcpyAsync(D.geoms_dev + D.geoms_uploaded, D.geoms_host.data() + D.geoms_uploaded,
+                       (D.geoms_host.size() - D.geoms_uploaded) * sizeof(FftGeom), cudaMemcpyHostToDevice, D.st));
     CK(cudaStreamSynchronize(D.st));
-    D.geoms_dirty = false;
+    D.geoms_uploaded = D.geoms_host.size();
     return ATSC_OK;
 }
 
 // ---------------------------------------------------------------- device setup
-int device_init(Device &D) {
-    CK(cudaSetDevice(D.id));
-    CK(cudaStreamCreateWithFlags(&D.st, cudaStreamNonBlocking));
-    int rc = kernels_init();
-    if (rc) {
-        D.err = std::string("kernels_init: ") + cudaGetErrorString((cudaError_t)rc);
-        return ATSC_ERR_CUDA;
-    }
-    int sms = 0;
-    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, D.id));
-    SlotPool &P = D.pool;
+int engine_init(Device &D, Engine &E, int sms) {
+    CK(cudaStreamCreateWithFlags(&E.st, cudaStreamNonBlocking));
+    SlotPool &P = E.pool;
     P.rle_slots = 2 * sms;
     P.fft_slots = 2 * sms;  // k_fft / k_decode run two 512-thread CTAs per SM
     P.dec_slots = 2 * sms;
+    P.fwd_slots = 2 * sms;  // k_fft_fwd: two 288-thread CTAs per SM (96 registers), each with its own W
     size_t rs = (size_t)P.rle_slots;
     CK(cudaMalloc((void **)&P.rle_k0, rs * MAX_FRAME * 8));
     CK(cudaMalloc((void **)&P.rle_k1, rs * MAX_FRAME * 8));
@@ -290,7 +327,7 @@ int device_init(Device &D) {
     CK(cudaMalloc((void **)&P.rle_i1, rs * MAX_FRAME * 4));
     CK(cudaMalloc((void **)&P.rle_bnd, rs * (MAX_FRAME + 8) * 4));
     size_t fs = (size_t)P.fft_slots, hb = MAX_FFT_LEN / 2 + 8;
-    CK(cudaMalloc((void **)&P.fft_W, fs * MAX_FFT_LEN * sizeof(float2)));
+    CK(cudaMalloc((void **)&P.fft_W, (size_t)std::max(P.fft_slots, P.fwd_slots) * MAX_FFT_LEN * sizeof(float2)));
     CK(cudaMalloc((void **)&P.fft_Xd, fs * hb * sizeof(float2)));
     CK(cudaMalloc((void **)&P.fft_keys, fs * hb * 4));
     CK(cudaMalloc((void **)&P.fft_rank, fs * hb * 4));
@@ -306,32 +343,65 @@ int device_init(Device &D) {
     CK(cudaMalloc((void **)&P.dec_pts, dsl * (MAX_FRAME + 8) * 8));
     CK(cudaMalloc((void **)&P.dec_mark, dsl * (MAX_FRAME + 8) * 4));
     CK(cudaMalloc((void **)&P.dec_idx, dsl * (MAX_FRAME + 8) * 4));
+    for (auto &e : E.ev) CK(cudaEventCreate(&e));
+    CK(cudaMalloc((void **)&E.queues, 64 * sizeof(unsigned)));
+    CK(cudaMalloc((void **)&E.d_ctl, sizeof(WaveCtl)));
+    CK(cudaMallocHost((void **)&E.h_ctl, sizeof(WaveCtl)));
+    return ATSC_OK;
+}
+
+int env_int(const char *name, int def, int lo, int hi) {
+    const char *v = getenv(name);
+    if (!v || !*v) return def;
+    int x = atoi(v);
+    return x < lo ? lo : x > hi ? hi : x;
+}
+
+int device_init(Device &D) {
+    CK(cudaSetDevice(D.id));
+    CK(cudaStreamCreateWithFlags(&D.st, cudaStreamNonBlocking));
+    int rc = kernels_init();
+    if (rc) {
+        D.err = std::string("kernels_init: ") + cudaGetErrorString((cudaError_t)rc);
+        return ATSC_ERR_CUDA;
+    }
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, D.id));
+    // waves in flight per device and samples per wave (tunable for experiments)
+    D.n_engines = env_int("ATSC_ENGINES", 3, 1, MAX_ENGINES);
+    D.wave_samples = (uint64_t)env_int("ATSC_WAVE_MI", 32, 1, 512) << 20;
+    for (int e = 0; e < D.n_engines; e++)
+        if ((rc = engine_init(D, D.eng[e], sms))) return rc;
+    CK(cudaMalloc((void **)&D.geoms_dev, GEOM_CAP * sizeof(FftGeom)));
     CK(cudaMalloc((void **)&D.inv_d2, (size_t)(MAX_FRAME + 8) * 8));
     launch_inv_d2(D.inv_d2, MAX_FRAME + 8, D.st);
     D.launches++;
-    for (auto &e : D.ev) CK(cudaEventCreate(&e));
-    CK(cudaMalloc((void **)&D.queues, 64 * sizeof(unsigned)));
-    CK(cudaMalloc((void **)&D.d_total, 8));
-    CK(cudaMallocHost((void **)&D.h_total, 8));
     CK(cudaStreamSynchronize(D.st));
     return ATSC_OK;
 }
 
 void device_free(Device &D) {
     cudaSetDevice(D.id);
-    SlotPool &P = D.pool;
-    void *ptrs[] = {P.rle_k0, P.rle_k1, P.rle_i0, P.rle_i1, P.rle_bnd, P.fft_W, P.fft_Xd, P.fft_keys, P.fft_rank,
-                    P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.poly_slope, P.dec_pts, P.dec_mark,
-                    P.dec_idx, D.inv_d2, D.queues, D.d_total, D.geoms_dev, D.d_frames, D.d_samples, D.d_arena,
-                    D.d_payload, D.d_dec, D.d_pay_in, D.d_out, D.d_status, D.d_spec_xd, D.d_spec_keys};
-    for (void *p : ptrs)
-        if (p) cudaFree(p);
+    cudaDeviceSynchronize();
+    for (int e = 0; e < D.n_engines; e++) {
+        Engine &E = D.eng[e];
+        SlotPool &P = E.pool;
+        void *ptrs[] = {P.rle_k0, P.rle_k1, P.rle_i0, P.rle_i1, P.rle_bnd, P.fft_W, P.fft_Xd, P.fft_keys, P.fft_rank,
+                        P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.poly_slope, P.dec_pts,
+                        P.dec_mark, P.dec_idx, E.queues, E.d_ctl, E.d_frames, E.d_samples, E.d_arena, E.d_payload,
+                        E.d_dec, E.d_pay_in, E.d_out, E.d_status, E.d_spec_xd, E.d_spec_keys};
+        for (void *p : ptrs)
+            if (p) cudaFree(p);
+        void *hp[] = {E.h_ctl, E.h_frames, E.h_dec, E.h_status};
+        for (void *p : hp)
+            if (p) cudaFreeHost(p);
+        for (auto &ev : E.ev)
+            if (ev) cudaEventDestroy(ev);
+        if (E.st) cudaStreamDestroy(E.st);
+    }
+    if (D.inv_d2) cudaFree(D.inv_d2);
+    if (D.geoms_dev) cudaFree(D.geoms_dev);
     for (void *p : D.geom_allocs) cudaFree(p);
-    void *hp[] = {D.h_total, D.h_frames, D.h_payload, D.h_dec, D.h_status};
-    for (void *p : hp)
-        if (p) cudaFreeHost(p);
-    for (auto &e : D.ev)
-        if (e) cudaEventDestroy(e);
     if (D.st) cudaStreamDestroy(D.st);
 }
 
@@ -345,29 +415,20 @@ bool is_device_ptr(const void *p) {
 }
 
 // ---------------------------------------------------------------- compress
-struct FrameReq {
-    uint64_t off;
-    uint32_t len;
-    uint8_t comp, bounded, select_only, forced;
-};
-
-// runs the pipeline for reqs[0..n) whose samples live at d_samples (device); results are left
-// in D.h_frames[0..n); payload bytes (if any) in D.h_payload[0..*payload_total)
-// direct_dst != nullptr: page-locked destination (capacity direct_cap) the payload is copied to
-// straight from the device; *direct is set when that happened (else the bytes are in D.h_payload)
-int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &reqs, float max_error_f32,
-             uint64_t *payload_total, uint8_t *direct_dst = nullptr, uint64_t direct_cap = 0, bool *direct = nullptr) {
-    if (direct) *direct = false;
+// Issues the whole pipeline of one wave on E's stream without waiting for it.  The frames'
+// samples live at d_samples (device).  collect_wave() picks the results up.
+int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<FrameReq> &reqs,
+               float max_error_f32) {
     const uint32_t n = (uint32_t)reqs.size();
     const double max_err = (double)max_error_f32;  // `max_error as f64` (frame/mod.rs:67,87)
     int rc;
-    size_t hcap = D.frames_cap;
-    if ((rc = grow(D, D.d_frames, D.frames_cap, n))) return rc;
-    if ((rc = grow(D, D.h_frames, hcap, D.frames_cap, true))) return rc;
-    uint64_t arena = 0, spec = 0;
+    size_t hcap = E.frames_cap;
+    if ((rc = grow(D, E.st, E.d_frames, E.frames_cap, n))) return rc;
+    if ((rc = grow(D, E.st, E.h_frames, hcap, E.frames_cap, true))) return rc;
+    uint64_t arena = 0, spec = 0, samples = 0;
     bool any_noop = false;
     for (uint32_t i = 0; i < n; i++) {
-        FrameWork &f = D.h_frames[i];
+        FrameWork &f = E.h_frames[i];
         memset(&f, 0, sizeof f);
         const FrameReq &r = reqs[i];
         f.off = r.off;
@@ -378,6 +439,7 @@ int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &re
         f.forced = r.forced;
         f.geom = -1;
         f.spec_off = ~0ull;
+        samples += r.len;
         uint8_t eff = (r.comp == C_AUTO && r.forced != 0xFF) ? r.forced : r.comp;
         any_noop |= r.comp == C_NOOP;
         if (eff == C_FFT || eff == C_AUTO) {
@@ -403,62 +465,75 @@ int run_wave(Device &D, const double *d_samples, const std::vector<FrameReq> &re
         }
     }
     if ((rc = sync_geoms(D))) return rc;
-    if ((rc = grow(D, D.d_arena, D.arena_cap, (size_t)arena + 1))) return rc;
-    if ((rc = grow(D, D.d_spec_xd, D.spec_xd_cap, (size_t)spec + 1))) return rc;
-    if ((rc = grow(D, D.d_spec_keys, D.spec_keys_cap, (size_t)spec + 1))) return rc;
-    CK(cudaMemcpyAsync(D.d_frames, D.h_frames, (size_t)n * sizeof(FrameWork), cudaMemcpyHostToDevice, D.st));
-    CK(cudaMemsetAsync(D.queues, 0, 64 * sizeof(unsigned), D.st));
-    CK(cudaEventRecord(D.ev[0], D.st));
-    launch_stats(D.d_frames, n, d_samples, D.queues + 0, D.st);
-    CK(cudaEventRecord(D.ev[1], D.st));
-    launch_plan(D.d_frames, n, D.st);
-    launch_poly(D.d_frames, n, d_samples, max_err, D.inv_d2, D.pool, D.queues + 1, D.st);
-    CK(cudaEventRecord(D.ev[2], D.st));
-    launch_rle(D.d_frames, n, d_samples, max_err, D.pool, D.queues + 2, D.st);
-    CK(cudaEventRecord(D.ev[3], D.st));
+    if ((rc = grow(D, E.st, E.d_arena, E.arena_cap, (size_t)arena + 1))) return rc;
+    if ((rc = grow(D, E.st, E.d_spec_xd, E.spec_xd_cap, (size_t)spec + 1))) return rc;
+    if ((rc = grow(D, E.st, E.d_spec_keys, E.spec_keys_cap, (size_t)spec + 1))) return rc;
+    // payload buffer sized before the total is known: one byte per sample covers every fleet but
+    // near-incompressible ones, which take the overflow path of collect_wave()
+    if ((rc = grow(D, E.st, E.d_payload, E.payload_cap, (size_t)std::max<uint64_t>(samples, 1u << 20) + 64 * (size_t)n))) return rc;
+    cudaStream_t st = E.st;
+    CK(cudaMemcpyAsync(E.d_frames, E.h_frames, (size_t)n * sizeof(FrameWork), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(E.queues, 0, 64 * sizeof(unsigned), st));
+    CK(cudaMemsetAsync(E.d_ctl, 0, sizeof(WaveCtl), st));
+    CK(cudaEventRecord(E.ev[0], st));
+    launch_stats(E.d_frames, n, d_samples, E.queues + 0, st);
+    CK(cudaEventRecord(E.ev[1], st));
+    launch_plan(E.d_frames, n, st);
+    launch_poly(E.d_frames, n, d_samples, max_err, D.inv_d2, E.pool, E.queues + 1, st);
+    CK(cudaEventRecord(E.ev[2], st));
+    launch_rle(E.d_frames, n, d_samples, max_err, E.pool, E.queues + 2, st);
+    CK(cudaEventRecord(E.ev[3], st));
     if (spec) {
-        launch_fft_fwd(D.d_frames, n, d_samples, max_err, D.geoms_dev, D.pool, D.d_spec_xd, D.d_spec_keys, D.queues + 7, D.st);
+        launch_fft_fwd(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_spec_xd, E.d_spec_keys, E.queues + 7, st);
         D.launches++;
     }
-    launch_fft(D.d_frames, n, d_samples, max_err, D.geoms_dev, D.pool, D.d_arena, D.d_spec_xd, D.d_spec_keys, D.queues + 3, D.st);
-    CK(cudaEventRecord(D.ev[4], D.st));
+    launch_fft(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_arena, E.d_spec_xd, E.d_spec_keys, E.queues + 3, st);
+    CK(cudaEventRecord(E.ev[4], st));
     D.launches += 5;
     if (any_noop) {
-        launch_noop_size(D.d_frames, n, d_samples, D.queues + 4, D.st);
+        launch_noop_size(E.d_frames, n, d_samples, E.queues + 4, st);
         D.launches++;
     }
-    launch_select(D.d_frames, n, max_err, D.st);
-    launch_scan(D.d_frames, n, D.d_total, D.st);
+    launch_select(E.d_frames, n, max_err, st);
+    launch_scan(E.d_frames, n, &E.d_ctl->total, st);
     D.launches += 2;
-    CK(cudaEventRecord(D.ev[5], D.st));
-    CK(cudaMemcpyAsync(D.h_total, D.d_total, 8, cudaMemcpyDeviceToHost, D.st));
-    CK(cudaStreamSynchronize(D.st));
+    CK(cudaEventRecord(E.ev[5], st));
+    CK(cudaEventRecord(E.ev[6], st));
+    launch_emit(E.d_frames, n, d_samples, D.geoms_dev, E.pool, E.d_arena, E.d_payload, &E.d_ctl->total,
+                (unsigned long long)E.payload_cap, &E.d_ctl->overflow, E.queues + 5, st);
+    CK(cudaEventRecord(E.ev[7], st));
+    D.launches++;
+    CK(cudaMemcpyAsync(E.h_frames, E.d_frames, (size_t)n * sizeof(FrameWork), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(E.h_ctl, E.d_ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
+    CK(cudaGetLastError());
+    return ATSC_OK;
+}
+
+// Waits for the wave issued on E; afterwards E.h_frames[0..n) hold the results and the wave's
+// payload bytes sit in E.d_payload[0..*payload_total) (the overflow path re-emits into a larger buffer).
+int wait_wave(Device &D, Engine &E, uint32_t n, const double *d_samples, uint64_t *payload_total) {
+    CK(cudaStreamSynchronize(E.st));
     CK(cudaGetLastError());
     for (int k = 0; k < 5; k++) {
         float t = 0.f;
-        CK(cudaEventElapsedTime(&t, D.ev[k], D.ev[k + 1]));
+        CK(cudaEventElapsedTime(&t, E.ev[k], E.ev[k + 1]));
         D.ms[k] += t;
     }
-    uint64_t total = *D.h_total;
+    float te = 0.f;
+    CK(cudaEventElapsedTime(&te, E.ev[6], E.ev[7]));
+    D.ms[5] += te;
+    const uint64_t total = E.h_ctl->total;
     *payload_total = total;
-    if (total) {
-        const bool to_user = direct_dst && total <= direct_cap;
-        if ((rc = grow(D, D.d_payload, D.payload_cap, (size_t)total + 16))) return rc;
-        if (!to_user && (rc = grow(D, D.h_payload, D.h_payload_cap, (size_t)total + 16, true))) return rc;
-        CK(cudaEventRecord(D.ev[6], D.st));
-        launch_emit(D.d_frames, n, d_samples, D.geoms_dev, D.pool, D.d_arena, D.d_payload, D.queues + 5, D.st);
-        CK(cudaEventRecord(D.ev[7], D.st));
+    if (E.h_ctl->overflow) {
+        int rc = grow(D, E.st, E.d_payload, E.payload_cap, (size_t)total + 64);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(E.queues + 5, 0, sizeof(unsigned), E.st));
+        CK(cudaMemsetAsync(&E.d_ctl->overflow, 0, sizeof(unsigned), E.st));
+        launch_emit(E.d_frames, n, d_samples, D.geoms_dev, E.pool, E.d_arena, E.d_payload, &E.d_ctl->total,
+                    (unsigned long long)E.payload_cap, &E.d_ctl->overflow, E.queues + 5, E.st);
         D.launches++;
-        CK(cudaMemcpyAsync(to_user ? direct_dst : D.h_payload, D.d_payload, (size_t)total, cudaMemcpyDeviceToHost, D.st));
-        if (direct) *direct = to_user;
-    }
-    CK(cudaMemcpyAsync(D.h_frames, D.d_frames, (size_t)n * sizeof(FrameWork), cudaMemcpyDeviceToHost, D.st));
-    CK(cudaStreamSynchronize(D.st));
-    CK(cudaGetLastError());
-    if (total) {
-        float t = 0.f;
-        CK(cudaEventElapsedTime(&t, D.ev[6], D.ev[7]));
-        D.ms[5] += t;
+        CK(cudaStreamSynchronize(E.st));
+        CK(cudaGetLastError());
     }
     return ATSC_OK;
 }
@@ -483,19 +558,39 @@ struct PayloadSink {
     uint8_t *buf;
     uint64_t cap, used;
     bool overflow;
-    bool pinned;  // buf is page-locked host memory: payloads are copied to it straight from the device
 };
 
-bool is_pinned_host(const void *p) {
-    cudaPointerAttributes a;
-    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return a.type == cudaMemoryTypeHost;
-}
-
 static const uint32_t COMPRESSION_SPEED[7] = {2147483647u, 4096, 2048, 1024, 512, 256, 128};  // frame/mod.rs:22
+
+// collects the wave pending on E: frame records -> out[], payload bytes -> sink (in wave order)
+int collect_wave(Device &D, Engine &E, const uint32_t *idx, atsc_frame_out *out, PayloadSink &sink) {
+    WaveJob &J = E.job;
+    if (!J.active) return ATSC_OK;
+    J.active = false;
+    uint64_t ptotal = 0;
+    int rc = wait_wave(D, E, J.n, J.d_samples, &ptotal);
+    if (rc) return rc;
+    for (uint32_t k = 0; k < J.n; k++) {
+        const FrameWork &f = E.h_frames[k];
+        atsc_frame_out &o = out[idx[J.pos + k]];
+        fill_out(f, o, sink.used);
+        if (J.sampled && J.reqs[k].forced != 0xFF && !f.is_const) {
+            o.near_tie |= J.tie1[k];
+            for (int c = 0; c < 3; c++) {
+                o.cand_error[c] = J.diag1[k].cand_error[c];
+                o.cand_size[c] = J.diag1[k].cand_size[c];
+            }
+        }
+    }
+    if (sink.used + ptotal > sink.cap)
+        sink.overflow = true;
+    else if (ptotal)
+        // page-locked destination: asynchronous, overlapped with the other engines' waves (the
+        // caller drains every stream before returning); pageable: staged by the runtime
+        CK(cudaMemcpyAsync(sink.buf + sink.used, E.d_payload, ptotal, cudaMemcpyDeviceToHost, E.st));
+    sink.used += ptotal;
+    return ATSC_OK;
+}
 
 // compress frames idx[0..m) on device D
 int compress_on_device(Device &D, const double *samples, bool dev_ptr, const uint64_t *frame_off,
@@ -504,9 +599,10 @@ int compress_on_device(Device &D, const double *samples, bool dev_ptr, const uin
     CK(cudaSetDevice(D.id));
     const bool sampled = bounded && compressor == C_AUTO && speed > 0;
     const uint32_t sample_n = COMPRESSION_SPEED[speed];
-    uint32_t pos = 0;
-    std::vector<FrameReq> reqs, sel;
+    uint32_t pos = 0, wave = 0;
+    std::vector<FrameReq> sel;
     std::vector<uint32_t> sel_of;
+    int rc = ATSC_OK;
     while (pos < m) {
         // ---- cut a wave
         uint64_t tot = 0;
@@ -514,35 +610,40 @@ int compress_on_device(Device &D, const double *samples, bool dev_ptr, const uin
         uint64_t lo = ~0ull, hi = 0;
         while (end < m && end - pos < WAVE_FRAMES) {
             uint32_t fi = idx[end];
-            if (tot && tot + frame_len[fi] > WAVE_SAMPLES) break;
+            if (tot && tot + frame_len[fi] > D.wave_samples) break;
             tot += frame_len[fi];
             lo = std::min(lo, frame_off[fi]);
             hi = std::max(hi, frame_off[fi] + frame_len[fi]);
             end++;
         }
         const uint32_t n = end - pos;
+        Engine &E = D.eng[wave % D.n_engines];
+        wave++;
+        // the engine's previous wave must be collected before its buffers are reused; waves are
+        // collected in issue order, so payloads land in frame order
+        if ((rc = collect_wave(D, E, idx, out, sink))) break;
         // ---- samples on the device
         const double *d_samples = samples;
         bool packed = false;
         if (!dev_ptr) {
             uint64_t span = hi - lo;
             packed = span > 2 * tot + 4096;
-            int rc = grow(D, D.d_samples, D.samples_cap, (size_t)(packed ? tot : span) + 8);
-            if (rc) return rc;
+            if ((rc = grow(D, E.st, E.d_samples, E.samples_cap, (size_t)(packed ? tot : span) + 8))) break;
             if (!packed) {
-                CK(cudaMemcpyAsync(D.d_samples, samples + lo, span * 8, cudaMemcpyHostToDevice, D.st));
+                CK(cudaMemcpyAsync(E.d_samples, samples + lo, span * 8, cudaMemcpyHostToDevice, E.st));
             } else {
                 uint64_t o = 0;
                 for (uint32_t k = pos; k < end; k++) {
                     uint32_t fi = idx[k];
-                    CK(cudaMemcpyAsync(D.d_samples + o, samples + frame_off[fi], (size_t)frame_len[fi] * 8,
-                                       cudaMemcpyHostToDevice, D.st));
+                    CK(cudaMemcpyAsync(E.d_samples + o, samples + frame_off[fi], (size_t)frame_len[fi] * 8,
+                                       cudaMemcpyHostToDevice, E.st));
                     o += frame_len[fi];
                 }
             }
-            d_samples = D.d_samples;
+            d_samples = E.d_samples;
         }
-        reqs.clear();
+        WaveJob &J = E.job;
+        J.reqs.clear();
         uint64_t po = 0;
         for (uint32_t k = pos; k < end; k++) {
             uint32_t fi = idx[k];
@@ -554,17 +655,18 @@ int compress_on_device(Device &D, const double *samples, bool dev_ptr, const uin
             r.bounded = bounded ? 1 : 0;
             r.select_only = 0;
             r.forced = 0xFF;
-            reqs.push_back(r);
+            J.reqs.push_back(r);
         }
-        std::vector<uint8_t> tie1(n, 0);
-        std::vector<atsc_frame_out> diag1;
+        J.sampled = sampled;
+        J.tie1.assign(n, 0);
+        J.diag1.clear();
         if (sampled) {
             // frame/mod.rs:89-111: pick the compressor on data[0..sample], then compress everything with it
             sel.clear();
             sel_of.clear();
             for (uint32_t k = 0; k < n; k++) {
-                if (reqs[k].len >= sample_n) {
-                    FrameReq r = reqs[k];
+                if (J.reqs[k].len >= sample_n) {
+                    FrameReq r = J.reqs[k];
                     r.len = sample_n;
                     r.select_only = 1;
                     sel.push_back(r);
@@ -573,48 +675,43 @@ int compress_on_device(Device &D, const double *samples, bool dev_ptr, const uin
             }
             if (!sel.empty()) {
                 uint64_t pt;
-                int rc = run_wave(D, d_samples, sel, max_error, &pt);
-                if (rc) return rc;
-                diag1.resize(n);
+                if ((rc = issue_wave(D, E, d_samples, sel, max_error))) break;
+                if ((rc = wait_wave(D, E, (uint32_t)sel.size(), d_samples, &pt))) break;
+                J.diag1.resize(n);
                 for (size_t s = 0; s < sel.size(); s++) {
-                    const FrameWork &f = D.h_frames[s];
-                    reqs[sel_of[s]].forced = f.winner;
-                    tie1[sel_of[s]] = f.near_tie;
-                    fill_out(f, diag1[sel_of[s]], 0);
+                    const FrameWork &f = E.h_frames[s];
+                    J.reqs[sel_of[s]].forced = f.winner;
+                    J.tie1[sel_of[s]] = f.near_tie;
+                    fill_out(f, J.diag1[sel_of[s]], 0);
                 }
+            } else {
+                J.diag1.resize(n);
             }
         }
-        uint64_t ptotal;
-        bool direct = false;
-        int rc = run_wave(D, d_samples, reqs, max_error, &ptotal, sink.pinned ? sink.buf + sink.used : nullptr,
-                          sink.pinned && sink.cap > sink.used ? sink.cap - sink.used : 0, &direct);
-        if (rc) return rc;
-        for (uint32_t k = 0; k < n; k++) {
-            const FrameWork &f = D.h_frames[k];
-            atsc_frame_out &o = out[idx[pos + k]];
-            fill_out(f, o, sink.used);
-            if (sampled && reqs[k].forced != 0xFF && !f.is_const) {
-                o.near_tie |= tie1[k];
-                for (int c = 0; c < 3; c++) {
-                    o.cand_error[c] = diag1[k].cand_error[c];
-                    o.cand_size[c] = diag1[k].cand_size[c];
-                }
-            }
-        }
-        if (sink.used + ptotal > sink.cap)
-            sink.overflow = true;
-        else if (ptotal && !direct)
-            memcpy(sink.buf + sink.used, D.h_payload, ptotal);
-        sink.used += ptotal;
+        if ((rc = issue_wave(D, E, d_samples, J.reqs, max_error))) break;
+        J.active = true;
+        J.pos = pos;
+        J.n = n;
+        J.d_samples = d_samples;
         pos = end;
     }
-    return ATSC_OK;
+    // ---- drain: collect the remaining waves in issue order, then wait for the payload copies
+    for (int k = 0; k < D.n_engines; k++) {
+        Engine &E = D.eng[(wave + k) % D.n_engines];
+        int rc2 = rc ? ATSC_OK : collect_wave(D, E, idx, out, sink);
+        if (rc2) rc = rc2;
+        E.job.active = false;
+    }
+    for (int k = 0; k < D.n_engines; k++) cudaStreamSynchronize(D.eng[k].st);
+    if (!rc) CK(cudaGetLastError());
+    return rc;
 }
 
 // ---------------------------------------------------------------- decompress
 int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t *idx, uint32_t m,
                          const uint8_t *payloads, uint64_t payload_bytes, double *out, bool out_dev) {
     CK(cudaSetDevice(D.id));
+    Engine &E = D.eng[0];
     uint32_t pos = 0;
     while (pos < m) {
         uint64_t tot = 0;
@@ -622,7 +719,7 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
         uint64_t plo = ~0ull, phi = 0;
         while (end < m && end - pos < WAVE_FRAMES) {
             const atsc_frame_in &f = frames[idx[end]];
-            if (tot && tot + f.sample_count > WAVE_SAMPLES) break;
+            if (tot && tot + f.sample_count > (48ull << 20)) break;
             tot += f.sample_count;
             plo = std::min<uint64_t>(plo, f.payload_off);
             phi = std::max<uint64_t>(phi, f.payload_off + f.payload_len);
@@ -634,18 +731,18 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
             return ATSC_ERR_ARG;
         }
         int rc;
-        size_t hc = D.dec_cap;
-        if ((rc = grow(D, D.d_dec, D.dec_cap, n))) return rc;
-        if ((rc = grow(D, D.h_dec, hc, D.dec_cap, true))) return rc;
-        hc = D.status_cap;
-        if ((rc = grow(D, D.d_status, D.status_cap, n))) return rc;
-        if ((rc = grow(D, D.h_status, hc, D.status_cap, true))) return rc;
-        if ((rc = grow(D, D.d_pay_in, D.pay_in_cap, (size_t)(phi - plo) + 64))) return rc;
-        if (!out_dev && (rc = grow(D, D.d_out, D.out_cap, (size_t)tot + 8))) return rc;
+        size_t hc = E.dec_cap;
+        if ((rc = grow(D, E.st, E.d_dec, E.dec_cap, n))) return rc;
+        if ((rc = grow(D, E.st, E.h_dec, hc, E.dec_cap, true))) return rc;
+        hc = E.status_cap;
+        if ((rc = grow(D, E.st, E.d_status, E.status_cap, n))) return rc;
+        if ((rc = grow(D, E.st, E.h_status, hc, E.status_cap, true))) return rc;
+        if ((rc = grow(D, E.st, E.d_pay_in, E.pay_in_cap, (size_t)(phi - plo) + 64))) return rc;
+        if (!out_dev && (rc = grow(D, E.st, E.d_out, E.out_cap, (size_t)tot + 8))) return rc;
         uint64_t oo = 0;
         for (uint32_t k = 0; k < n; k++) {
             const atsc_frame_in &f = frames[idx[pos + k]];
-            DecFrame &d = D.h_dec[k];
+            DecFrame &d = E.h_dec[k];
             memset(&d, 0, sizeof d);
             d.payload_off = f.payload_off - plo;
             d.payload_len = f.payload_len;
@@ -665,15 +762,15 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
             }
         }
         if ((rc = sync_geoms(D))) return rc;
-        CK(cudaMemcpyAsync(D.d_dec, D.h_dec, (size_t)n * sizeof(DecFrame), cudaMemcpyHostToDevice, D.st));
-        CK(cudaMemcpyAsync(D.d_pay_in, payloads + plo, (size_t)(phi - plo), cudaMemcpyHostToDevice, D.st));
-        CK(cudaMemsetAsync(D.queues, 0, 64 * sizeof(unsigned), D.st));
-        double *d_out = out_dev ? out : D.d_out;
-        CK(cudaEventRecord(D.ev[8], D.st));
-        launch_decode(D.d_dec, n, D.d_pay_in, d_out, D.geoms_dev, D.pool, D.inv_d2, D.d_status, D.queues + 6, D.st);
-        CK(cudaEventRecord(D.ev[9], D.st));
+        CK(cudaMemcpyAsync(E.d_dec, E.h_dec, (size_t)n * sizeof(DecFrame), cudaMemcpyHostToDevice, E.st));
+        CK(cudaMemcpyAsync(E.d_pay_in, payloads + plo, (size_t)(phi - plo), cudaMemcpyHostToDevice, E.st));
+        CK(cudaMemsetAsync(E.queues, 0, 64 * sizeof(unsigned), E.st));
+        double *d_out = out_dev ? out : E.d_out;
+        CK(cudaEventRecord(E.ev[8], E.st));
+        launch_decode(E.d_dec, n, E.d_pay_in, d_out, D.geoms_dev, E.pool, D.inv_d2, E.d_status, E.queues + 6, E.st);
+        CK(cudaEventRecord(E.ev[9], E.st));
         D.launches++;
-        CK(cudaMemcpyAsync(D.h_status, D.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, D.st));
+        CK(cudaMemcpyAsync(E.h_status, E.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, E.st));
         if (!out_dev) {
             // coalesce frames that are adjacent in the caller's output
             uint32_t k = 0;
@@ -686,24 +783,24 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
                     len += frames[idx[pos + j]].sample_count;
                     j++;
                 }
-                CK(cudaMemcpyAsync(out + dst, D.d_out + src, len * 8, cudaMemcpyDeviceToHost, D.st));
+                CK(cudaMemcpyAsync(out + dst, E.d_out + src, len * 8, cudaMemcpyDeviceToHost, E.st));
                 src += len;
                 k = j;
             }
         }
-        CK(cudaStreamSynchronize(D.st));
+        CK(cudaStreamSynchronize(E.st));
         CK(cudaGetLastError());
         {
             float t = 0.f;
-            CK(cudaEventElapsedTime(&t, D.ev[8], D.ev[9]));
+            CK(cudaEventElapsedTime(&t, E.ev[8], E.ev[9]));
             D.ms[6] += t;
         }
         for (uint32_t k = 0; k < n; k++)
-            if (D.h_status[k]) {
+            if (E.h_status[k]) {
                 char b[128];
-                snprintf(b, sizeof b, "frame %u: malformed or unsupported payload (code %u)", idx[pos + k], D.h_status[k]);
+                snprintf(b, sizeof b, "frame %u: malformed or unsupported payload (code %u)", idx[pos + k], E.h_status[k]);
                 D.err = b;
-                return D.h_status[k] == 4 ? ATSC_ERR_UNSUPPORTED : ATSC_ERR_FORMAT;
+                return E.h_status[k] == 4 ? ATSC_ERR_UNSUPPORTED : ATSC_ERR_FORMAT;
             }
         pos = end;
     }
@@ -823,7 +920,7 @@ int atsc_gpu_compress_frames(atsc_ctx *ctx, const double *samples, const uint64_
     if (nd == 1) {
         std::vector<uint32_t> idx(n_frames);
         for (uint32_t i = 0; i < n_frames; i++) idx[i] = i;
-        PayloadSink sink{payload_buf, payload_cap, 0, false, is_pinned_host(payload_buf)};
+        PayloadSink sink{payload_buf, payload_cap, 0, false};
         Device &D = *ctx->devs[0];
         int rc = compress_on_device(D, samples, dev_ptr, frame_off, frame_len, idx.data(), n_frames, compressor,
                                     max_error, speed, bounded, out, sink);
@@ -848,7 +945,7 @@ int atsc_gpu_compress_frames(atsc_ctx *ctx, const double *samples, const uint64_
         uint64_t cap = 0;
         for (uint32_t i : parts[d]) cap += (uint64_t)frame_len[i] * 16 + 64;  // worst case: RLE of all-distinct f64
         bufs[d].resize(cap);
-        sinks[d] = PayloadSink{bufs[d].data(), cap, 0, false, false};
+        sinks[d] = PayloadSink{bufs[d].data(), cap, 0, false};
         th.emplace_back([&, d]() {
             if (parts[d].empty()) return;
             rcs[d] = compress_on_device(*ctx->devs[d], samples, false, frame_off, frame_len, parts[d].data(),

@@ -133,9 +133,14 @@ struct DftS<27, S, INV> {
     static __device__ __forceinline__ void run(float2 *a) { dft_comp<3, 9, S, INV>(a); }
 };
 
-// padded ("gibbs sized") complex element n of the frame: (x[2n], x[2n+1]) as f32 (fft.rs:184-228)
-__device__ __forceinline__ float2 f2_load_z(const double *__restrict__ d, int N, int prefix, int n) {
+// padded ("gibbs sized") complex element n of the frame: (x[2n], x[2n+1]) as f32 (fft.rs:184-228).
+// `vec`: d + (2n - prefix) is 16-byte aligned for every n, so interior elements take one 128-bit load.
+__device__ __forceinline__ float2 f2_load_z(const double *__restrict__ d, int N, int prefix, int n, bool vec) {
     int i0 = 2 * n - prefix, i1 = i0 + 1;
+    if (vec && i0 >= 0 && i1 < N) {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(d + i0));
+        return make_float2((float)v.x, (float)v.y);
+    }
     i0 = min(max(i0, 0), N - 1);
     i1 = min(max(i1, 0), N - 1);
     return make_float2((float)__ldg(d + i0), (float)__ldg(d + i1));
@@ -149,6 +154,7 @@ __device__ inline void f2_pass1(const double *__restrict__ d, int N, int prefix,
                                 const float2 *__restrict__ T4, float2 *W, float2 *sm) {
     constexpr int M1 = RA * RB, P1 = M1 + 1;  // odd pitch: the column-strided stores are conflict free
     const int tid = threadIdx.x, nth = blockDim.x;
+    const bool vec = (((uintptr_t)d >> 3) & 1u) == ((uint32_t)prefix & 1u);
     for (int c0 = 0; c0 < F2_M2; c0 += F2_TC) {
         const int nb = min(F2_TC, F2_M2 - c0);
         // stage 1: item (p < RB, column lc): radix RA over rows p + RB*t, Stockham twiddle W_M1^(p q)
@@ -157,7 +163,7 @@ __device__ inline void f2_pass1(const double *__restrict__ d, int N, int prefix,
             if (lc >= nb) continue;
             float2 a[RA];
 #pragma unroll
-            for (int t = 0; t < RA; t++) a[t] = f2_load_z(d, N, prefix, (p + RB * t) * F2_M2 + c0 + lc);
+            for (int t = 0; t < RA; t++) a[t] = f2_load_z(d, N, prefix, (p + RB * t) * F2_M2 + c0 + lc, vec);
             DftS<RA, 1, false>::run(a);
             float2 *y = sm + lc * P1 + RA * p;
             y[0] = a[0];

@@ -649,10 +649,18 @@ __device__ void emit_noop(const double *__restrict__ d, const FrameWork *fw, uin
 
 __global__ void __launch_bounds__(BLOCK) k_emit(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
                                                 const FftGeom *__restrict__ geoms, SlotPool pool,
-                                                const FftEntry *__restrict__ arena, uint8_t *payload, unsigned *q) {
+                                                const FftEntry *__restrict__ arena, uint8_t *payload,
+                                                const unsigned long long *total, unsigned long long cap,
+                                                unsigned *overflow, unsigned *q) {
     extern __shared__ uint32_t dyn_hist[];
     __shared__ double shd[64];
     __shared__ int s_item;
+    // the wave's payload (k_scan's total) must fit the device buffer the host sized before it knew
+    // the total; otherwise nothing is written and the host grows the buffer and launches again
+    if (*total > cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1u;
+        return;
+    }
     uint32_t *sh = (uint32_t *)shd;
     RleWs ws = rle_slot(pool, blockIdx.x);
     for (;;) {
@@ -1085,7 +1093,7 @@ void launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err
 }
 void launch_fft_fwd(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
                     SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st) {
-    k_fft_fwd<<<grid_for(n, pool.fft_slots), F2_THREADS, F2_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool,
+    k_fft_fwd<<<grid_for(n, pool.fwd_slots), F2_THREADS, F2_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool,
                                                                              spec_xd, spec_keys, q);
 }
 void launch_noop_size(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st) {
@@ -1098,8 +1106,10 @@ void launch_scan(FrameWork *fr, uint32_t n, unsigned long long *total, cudaStrea
     k_scan<<<1, BLOCK, 0, st>>>(fr, n, total);
 }
 void launch_emit(FrameWork *fr, uint32_t n, const double *samples, const FftGeom *geoms, SlotPool pool,
-                 const FftEntry *arena, uint8_t *payload, unsigned *q, cudaStream_t st) {
-    k_emit<<<grid_for(n, pool.rle_slots), BLOCK, RLE_HIST_WORDS * 4, st>>>(fr, n, samples, geoms, pool, arena, payload, q);
+                 const FftEntry *arena, uint8_t *payload, const unsigned long long *total, unsigned long long cap,
+                 unsigned *overflow, unsigned *q, cudaStream_t st) {
+    k_emit<<<grid_for(n, pool.rle_slots), BLOCK, RLE_HIST_WORDS * 4, st>>>(fr, n, samples, geoms, pool, arena, payload,
+                                                                          total, cap, overflow, q);
 }
 void launch_decode(const DecFrame *fr, uint32_t n, const uint8_t *payloads, double *out, const FftGeom *geoms,
                    SlotPool pool, const double *inv_d2, uint32_t *status, unsigned *q, cudaStream_t st) {

@@ -20,6 +20,7 @@ struct SlotPool {
     uint32_t *fft_keys, *fft_rank, *fft_locD, *fft_locM, *fft_ovr;
     FftEntry *fft_dlist;
     int fft_slots;
+    int fwd_slots;  // CTAs of k_fft_fwd (they use fft_W only)
     // polynomial refinement loop (poly.cuh)
     double *poly_slope;  // [MAX_FRAME + 8] per slot
     int poly_slots;
@@ -54,8 +55,10 @@ void launch_fft_fwd(FrameWork *fr, uint32_t n, const double *samples, double max
 void launch_noop_size(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st);
 void launch_select(FrameWork *fr, uint32_t n, double max_err, cudaStream_t st);
 void launch_scan(FrameWork *fr, uint32_t n, unsigned long long *total, cudaStream_t st);
+// writes nothing and raises *overflow when *total (k_scan's result) exceeds cap
 void launch_emit(FrameWork *fr, uint32_t n, const double *samples, const FftGeom *geoms, SlotPool pool,
-                 const FftEntry *arena, uint8_t *payload, unsigned *q, cudaStream_t st);
+                 const FftEntry *arena, uint8_t *payload, const unsigned long long *total, unsigned long long cap,
+                 unsigned *overflow, unsigned *q, cudaStream_t st);
 // decompress
 void launch_decode(const DecFrame *fr, uint32_t n, const uint8_t *payloads, double *out,
                    const FftGeom *geoms, SlotPool pool, const double *inv_d2, uint32_t *status,
