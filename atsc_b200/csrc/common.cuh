@@ -189,6 +189,37 @@ __device__ inline double round_f64_dec(double x, int decimals) {
     return __ddiv_rn(round(__dmul_rn(x, y)), y);
 }
 
+// f64::round (half away from zero) without the library call: trunc + exact remainder test
+__device__ __forceinline__ double round_half_away(double y) {
+    double r = trunc(y);
+    double diff = __dsub_rn(y, r);  // exact
+    if (fabs(diff) >= 0.5) r = __dadd_rn(r, copysign(1.0, y));
+    return r;
+}
+// n / 100000.0, correctly rounded, for the integer-valued n that `round()` returns: Markstein's
+// two-step FMA refinement of n * RN(1/100000) (q1 is already faithful, q2 is the IEEE quotient;
+// checked against the hardware division on 4e8 random integers of every width up to 53 bits).
+// Branch free: +-inf (where the refinement would produce NaN) is passed through by a select.
+__device__ __forceinline__ double div_1e5(double n) {
+    const double b = 100000.0, y = 1e-5;
+    double q = __dmul_rn(n, y);
+    q = __fma_rn(__fma_rn(-b, q, n), y, q);
+    q = __fma_rn(__fma_rn(-b, q, n), y, q);
+    return fabs(n) == __longlong_as_double(0x7FF0000000000000ll) ? n : q;
+}
+// 1 / o to within 1 ulp, branch free (the error loops tolerate that, see mape_term): hardware seed
+// (2^-23) + two Newton steps.  o == 0 or denormal -> the seed itself (+-inf), like the IEEE quotient
+// of a zero sample; inf / NaN propagate through the seed as well.
+__device__ __forceinline__ double rcp_1ulp(double o) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(o));
+    double e = __fma_rn(-o, y, 1.0);
+    double y1 = __fma_rn(y, e, y);
+    e = __fma_rn(-o, y1, 1.0);
+    y1 = __fma_rn(y1, e, y1);
+    return (y1 == y1 && fabs(y) != __longlong_as_double(0x7FF0000000000000ll) && y != 0.0) ? y1 : y;
+}
+
 // optimizer/utils.rs:115-160 split_n: (integer part as i64, fraction != 0)
 __device__ inline int64_t split_n(double x, bool *frac_nz) {
     uint64_t bits = (uint64_t)__double_as_longlong(x);

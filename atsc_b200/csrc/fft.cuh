@@ -740,12 +740,10 @@ __device__ inline double fft_round(float x, float vminf, float vmaxf) {
     return out;
 }
 
-// same, for the refinement loop only: `* 1e-5` instead of the true `/ 1e5` (<= 1 ulp off; the error
-// it feeds is compared against thresholds)
-__device__ inline double fft_round_fast(float x, double o, float vminf, float vmaxf) {
-    double n = round(__dmul_rn((double)x, 100000.0));
-    double out = n * 1e-5;
-    if (fabs(out - o) <= fabs(o) * 4.5e-16) out = __ddiv_rn(n, 100000.0);  // exact zero terms stay exact
+// same value through the FMA-refined quotient (poly.cuh div_1e5), for the refinement loop
+__device__ inline double fft_round_fast(float x, float vminf, float vmaxf) {
+    double n = round_half_away(__dmul_rn((double)x, 100000.0));
+    double out = div_1e5(n);
     if (out > (double)vmaxf) return (double)vmaxf;
     if (out < (double)vminf) return (double)vminf;
     return out;

@@ -171,6 +171,15 @@ __device__ inline void f2_pass1(const double *__restrict__ d, int N, int prefix,
             for (int q = 1; q < RA; q++) y[q] = cmul(a[q], __ldg(tw1 + p * q));
         }
         __syncthreads();
+        // L2 prefetch of the next tile's samples (M1 rows x 512 B) while this tile finishes
+        if (c0 + F2_TC < F2_M2) {
+            for (int i = tid; i < M1 * 4; i += nth) {
+                const int e = i >> 2, ln = i & 3;
+                int ix = 2 * (e * F2_M2 + c0 + F2_TC) - prefix + 16 * ln;
+                ix = min(max(ix, 0), N - 1);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(d + ix));
+            }
+        }
         // stage 2: item (q < RA, column lc), q fastest: radix RB over y[q + RA*t] -> k1 = q + RA*u
         for (int item = tid; item < RA * F2_TC; item += nth) {
             const int q = item % RA, lc = item / RA;

@@ -98,7 +98,6 @@ __global__ void __launch_bounds__(BLOCK) k_poly(FrameWork *fr, uint32_t n, const
                                                 double max_err, const double *__restrict__ inv_d2, SlotPool pool,
                                                 unsigned *q) {
     __shared__ double shd[64];
-    __shared__ PolyTab tab;
     __shared__ int s_item;
     PolyWs ws;
     ws.slope = pool.poly_slope + (size_t)blockIdx.x * (MAX_FRAME + 8);
@@ -107,7 +106,7 @@ __global__ void __launch_bounds__(BLOCK) k_poly(FrameWork *fr, uint32_t n, const
         if (i >= (int)n) break;
         FrameWork *fw = &fr[i];
         if (!fw->need_poly) continue;
-        poly_frame(samples + fw->off, fw, max_err, inv_d2, shd, ws, &tab);
+        poly_frame(samples + fw->off, fw, max_err, inv_d2, shd, ws);
     }
 }
 
@@ -296,7 +295,7 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
             uint32_t ix = j < prefix ? 0u : j - prefix;  // gibbs padding replicates the edge samples
             if (ix >= N) ix = N - 1;
             const double o = d[ix];
-            double out = fft_round_fast(__fdiv_rn(v, Lf), o, vminf, vmaxf);
+            double out = fft_round_fast(__fdiv_rn(v, Lf), vminf, vmaxf);
             acc += mape_term(out, o);
         };
         if (gi >= 0) {

@@ -92,126 +92,108 @@ __device__ inline double idw_eval_at(const PolyKeys &k, uint32_t x, PtsFn pts,
 struct PolyWs {
     double *slope;  // [MAX_FRAME + 8] tangent (central-difference slope * step) at every key of the current step
 };
-constexpr int POLY_TAB = 136;  // step <= 133 (polynomial.rs:290 with >= max(3, N/100) points)
-struct PolyTab {
-    double lin0[POLY_TAB];  // 1 - t
-    double tt[POLY_TAB];    // t = j / step
-    double h00[POLY_TAB], h10[POLY_TAB], h01[POLY_TAB], h11[POLY_TAB];  // cubic Hermite basis at t
-};
+constexpr int POLY_MAXSTEP = 136;  // step <= 133 (polynomial.rs:290 with >= max(3, N/100) points)
 
-// f64::round (half away from zero) without the library call: trunc + exact remainder test
-__device__ inline double round_half_away(double y) {
-    double r = trunc(y);
-    double diff = __dsub_rn(y, r);  // exact
-    if (fabs(diff) >= 0.5) r = __dadd_rn(r, copysign(1.0, y));
-    return r;
-}
-
-// One MAPE term |(out - o) / o| (utils/error.rs:110-113) through the reciprocal w = 1/o (IEEE):
-// deviates from the true division by <= 1 ulp (absorbed by the near-tie tolerance, the error only
-// feeds threshold tests) while exact zeros stay exactly zero.  A zero sample keeps the
-// reference's semantics: w = inf gives |out * inf - 1| = inf (out != 0) or NaN (out == 0), SURVEY H5.
-__device__ inline double mape_term(double out, double o, double w) {
-    return (out == o && o != 0.0) ? 0.0 : fabs(fma(out, w, -1.0));
-}
-__device__ inline double mape_term(double out, double o) { return mape_term(out, o, __drcp_rn(o)); }
-// (x * 1e5).round() / 1e5 for the error loops.  `* 1e-5` replaces the true division (<= 1 ulp off)
-// unless the result lands within 2 ulp of the original sample `o`: an exactly reproduced sample
-// must give an exactly zero error term (lossless `-e 0` relies on `error <= 0`), so that case
-// takes the IEEE quotient.  Only the decompressor always needs the exact quotient.
-__device__ inline double round5_loop(double x, double o) {
+// utils/mod.rs:66-74 round_and_limit_f64(x, min, max, 5), same value as round_and_limit5
+__device__ __forceinline__ double round_and_limit5_fast(double x, double mn, double mx) {
     double n = round_half_away(__dmul_rn(x, 100000.0));
-    double out = n * 1e-5;
-    if (fabs(out - o) <= fabs(o) * 4.5e-16) out = __ddiv_rn(n, 100000.0);
-    return out;
-}
-__device__ inline double round_and_limit5_fast(double x, double o, double mn, double mx) {
-    double out = round5_loop(x, o);
+    double out = div_1e5(n);
     if (out < mn) return mn;
     if (out > mx) return mx;
     return out;
 }
 
+// One MAPE term |(out - o) / o| (utils/error.rs:110-113) through the reciprocal w = RN(1/o): within
+// 1 ulp of the true quotient (absorbed by the near-tie tolerance, the error only feeds threshold
+// tests); an exactly reproduced sample gives exactly 0.  A zero sample keeps the reference's
+// semantics: w = inf gives inf (out != 0) or NaN (out == 0), SURVEY H5.
+__device__ __forceinline__ double mape_term(double out, double o) {
+    return fabs(__dmul_rn(__dsub_rn(out, o), rcp_1ulp(o)));
+}
+
 // MAPE (utils/error.rs:104-116) of one candidate step against the frame; block-wide.
-// Catmull-Rom path: identical value arithmetic to poly_eval_at (same operations, same order),
-// but everything that depends only on the offset inside a segment comes from a table and the
-// per-key tangents from a pre-pass, so the inner loop has no division besides the reciprocal
-// of the sample.
+// Catmull-Rom path: identical value arithmetic to poly_eval_at (same operations, same order).
+// Thread t owns one offset j inside the segments (its Hermite basis values stay in registers) and
+// walks over segments, so the inner loop has no table lookups, no index division and no branches;
+// the per-key tangents come from a pre-pass.
 __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys &k, int ptype,
                                    double vmin, double vmax, const double *__restrict__ inv_d2,
-                                   PolyWs ws, PolyTab *tab, double *scratch) {
+                                   PolyWs ws, double *scratch) {
     const uint32_t N = k.N, step = k.step, K = k.K, T = blockDim.x, t = threadIdx.x;
     double acc = 0.0;
     auto pts = [&](uint32_t j) { return d[poly_pos(k, j)]; };
-    if (ptype || step >= (uint32_t)POLY_TAB || K < 2) {
+    if (ptype || step >= (uint32_t)POLY_MAXSTEP || K < 2) {
         for (uint32_t x = t; x < N; x += T) {
             double v = ptype ? idw_eval_at(k, x, pts, inv_d2) : poly_eval_at(k, x, pts);
             double o = d[x];
-            double out = round_and_limit5_fast(v, o, vmin, vmax);
-            acc += mape_term(out, o);
+            acc += mape_term(round_and_limit5_fast(v, vmin, vmax), o);
         }
         double s = block_sum(acc, scratch);
         return __ddiv_rn(s, (double)N);
     }
-    // ---- tables over the offset j inside a regular segment
-    const double stepd = (double)step;
-    for (uint32_t j = t; j < step; j += T) {
-        double tt = __ddiv_rn((double)j, stepd);
-        double two_t = __dmul_rn(tt, 2.0), three_t = __dmul_rn(tt, 3.0);
-        double t2 = __dmul_rn(tt, tt), t3 = __dmul_rn(t2, tt);
-        double two_t3 = __dmul_rn(t2, two_t), two_t2 = __dmul_rn(tt, two_t), three_t2 = __dmul_rn(tt, three_t);
-        tab->tt[j] = tt;
-        tab->lin0[j] = __dsub_rn(1.0, tt);
-        tab->h00[j] = __dadd_rn(__dsub_rn(two_t3, three_t2), 1.0);
-        tab->h10[j] = __dadd_rn(__dsub_rn(t3, two_t2), tt);
-        tab->h01[j] = __dsub_rn(three_t2, two_t3);
-        tab->h11[j] = __dsub_rn(t3, t2);
-    }
     // ---- tangent at every interior key: (v[j+1] - v[j-1]) / (pos[j+1] - pos[j-1]) * step
     // (both segments that use it as a Catmull-Rom tangent are regular, i.e. `step` long)
+    const double stepd = (double)step;
     double *__restrict__ tang = ws.slope;
     for (uint32_t j = 1 + t; j + 1 < K; j += T) {
         uint32_t pa = poly_pos(k, j - 1), pb = poly_pos(k, j + 1);
         tang[j] = __dmul_rn(__ddiv_rn(__dsub_rn(d[pb], d[pa]), __dsub_rn((double)pb, (double)pa)), stepd);
     }
     __syncthreads();
+    // ---- Catmull-Rom segments 1 .. K-3 (polynomial.rs:349: key i is CatmullRom iff 0 < i < K-2)
+    const uint32_t G = T / step, g = t / step, j = t - g * step;  // G groups of `step` threads
+    if (g < G && K >= 4) {
+        const double tt = __ddiv_rn((double)j, stepd);
+        const double two_t = __dmul_rn(tt, 2.0), three_t = __dmul_rn(tt, 3.0);
+        const double t2 = __dmul_rn(tt, tt), t3 = __dmul_rn(t2, tt);
+        const double two_t3 = __dmul_rn(t2, two_t), two_t2 = __dmul_rn(tt, two_t), three_t2 = __dmul_rn(tt, three_t);
+        const double h00 = __dadd_rn(__dsub_rn(two_t3, three_t2), 1.0), h10 = __dadd_rn(__dsub_rn(t3, two_t2), tt);
+        const double h01 = __dsub_rn(three_t2, two_t3), h11 = __dsub_rn(t3, t2);
+        const uint32_t i_hi = K - 3;  // inclusive; keys i and i+1 are regular for every i <= K-3
+        // two segments per trip: their (long, strictly serial) f64 chains are independent, and with
+        // every helper branch free the compiler interleaves them
+        for (uint32_t i = 1 + g; i <= i_hi; i += 2 * G) {
+            const uint32_t i2 = i + G;
+            const bool two = i2 <= i_hi;
+            const uint32_t xa = i * step, xb = (two ? i2 : i) * step;
+            const double o = d[xa + j], av = d[xa], bv = d[xa + step], ta = tang[i], tb = tang[i + 1];
+            const double o2 = d[xb + j], av2 = d[xb], bv2 = d[xb + step], ta2 = tang[two ? i2 : i], tb2 = tang[(two ? i2 : i) + 1];
+            const double v = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(av, h00), __dmul_rn(ta, h10)), __dmul_rn(bv, h01)),
+                                       __dmul_rn(tb, h11));
+            const double v2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(av2, h00), __dmul_rn(ta2, h10)), __dmul_rn(bv2, h01)),
+                                        __dmul_rn(tb2, h11));
+            const double e1 = mape_term(round_and_limit5_fast(v, vmin, vmax), o);
+            const double e2 = mape_term(round_and_limit5_fast(v2, vmin, vmax), o2);
+            acc += e1;
+            if (two) acc += e2;
+        }
+    }
+    // ---- the Linear ends: segment 0, segment K-2 (possibly irregular) and the last sample
     const uint32_t Kreg = k.Kreg;
     const uint32_t last_reg = (Kreg - 1) * step;  // position of the last regular key
-    const uint32_t magic = (uint32_t)((0x100000000ull + step - 1) / step);  // x / step == umulhi(x, magic), x < 2^17
-    constexpr int U = 4;  // samples in flight per thread: their loads are issued before any arithmetic
-    for (uint32_t x0 = t; x0 < N; x0 += U * T) {
-        double o[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) o[u] = (x0 + u * T < N) ? d[x0 + u * T] : 1.0;
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t x = x0 + u * T;
-            if (x >= N) break;
-            const uint32_t i = __umulhi(x, magic), j = x - i * step;
-            double v;
-            if (i >= 1 && i + 2 < K) {
-                // regular Catmull-Rom segment (polynomial.rs:349: key i is CatmullRom iff 0 < i < K-2)
-                const double av = d[i * step], bv = d[(i + 1) * step];
-                double c0 = __dmul_rn(av, tab->h00[j]);
-                double c1 = __dmul_rn(tang[i], tab->h10[j]);
-                double c2 = __dmul_rn(bv, tab->h01[j]);
-                double c3 = __dmul_rn(tang[i + 1], tab->h11[j]);
-                v = __dadd_rn(__dadd_rn(__dadd_rn(c0, c1), c2), c3);
-            } else if (x == N - 1) {
-                v = d[N - 1];
-            } else if (i == Kreg - 1) {
-                // irregular last segment [last_reg, N-1]: always Linear (it is segment K-2)
-                double at = (double)last_reg, bt = (double)(N - 1);
-                double nt = __ddiv_rn(__dsub_rn((double)x, at), __dsub_rn(bt, at));
-                v = __dadd_rn(__dmul_rn(d[last_reg], __dsub_rn(1.0, nt)), __dmul_rn(d[N - 1], nt));
-            } else {
-                // first segment, or the regular segment K-2: Linear
-                const uint32_t pb = (i + 1 < Kreg) ? (i + 1) * step : N - 1;
-                v = __dadd_rn(__dmul_rn(d[i * step], tab->lin0[j]), __dmul_rn(d[pb], tab->tt[j]));
-            }
-            const double out = round_and_limit5_fast(v, o[u], vmin, vmax);
-            acc += mape_term(out, o[u]);
+    const uint32_t start_last = (K >= 4) ? (K - 2) * step : 0u;  // K < 4: no Catmull-Rom segment at all
+    const uint32_t nA = min(step, start_last), nB = N - start_last;
+    for (uint32_t e = t; e < nA + nB; e += T) {
+        const uint32_t x = e < nA ? e : start_last + (e - nA);
+        const uint32_t i = x / step, jj = x - i * step;
+        double v;
+        if (x == N - 1) {
+            v = d[N - 1];
+        } else if (i == Kreg - 1) {
+            // irregular last segment [last_reg, N-1]: always Linear (it is segment K-2)
+            double at = (double)last_reg, bt = (double)(N - 1);
+            double nt = __ddiv_rn(__dsub_rn((double)x, at), __dsub_rn(bt, at));
+            v = __dadd_rn(__dmul_rn(d[last_reg], __dsub_rn(1.0, nt)), __dmul_rn(d[N - 1], nt));
+        } else if (i >= 1 && i + 2 < K) {
+            // only reached when K < 4 cannot happen (then no such i exists); kept for completeness
+            v = poly_eval_at(k, x, pts);
+        } else {
+            // first segment, or the regular segment K-2: Linear  a * (1 - t) + b * t
+            const uint32_t pb = (i + 1 < Kreg) ? (i + 1) * step : N - 1;
+            const double nt = __ddiv_rn((double)jj, stepd);
+            v = __dadd_rn(__dmul_rn(d[i * step], __dsub_rn(1.0, nt)), __dmul_rn(d[pb], nt));
         }
+        acc += mape_term(round_and_limit5_fast(v, vmin, vmax), d[x]);
     }
     double s = block_sum(acc, scratch);
     return __ddiv_rn(s, (double)N);
@@ -246,7 +228,7 @@ __device__ inline bool poly_loop_near_tie(double cur, double target) {
 // Runs the reference's refinement loop for one frame. All threads of the CTA call.
 // Writes poly_* fields of fw (thread 0).  `sh` = shared scratch (>= 40 doubles).
 __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, double max_err,
-                                  const double *__restrict__ inv_d2, double *sh, PolyWs ws, PolyTab *tab) {
+                                  const double *__restrict__ inv_d2, double *sh, PolyWs ws) {
     const uint32_t N = fw->len;
     const double vmin = fw->vmin, vmax = fw->vmax;
     const int ptype = fw->poly_type;
@@ -279,7 +261,7 @@ __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, d
                 } else if (step == 1 && it <= 22) {
                     cur = 0.0;  // value unused: the `len == data_len` exit below overrides it
                 } else {
-                    cur = poly_mape(d, k, ptype, vmin, vmax, inv_d2, ws, tab, sh);
+                    cur = poly_mape(d, k, ptype, vmin, vmax, inv_d2, ws, sh);
                 }
                 prev_step = step;
                 prev_err = cur;

@@ -1,0 +1,3 @@
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py --steps 5 --warmup 3 --series 96 --no-cpu 2>&1 | python tools/benchline.py
+ATSC_ENGINES=1 ATSC_WAVE_MI=48 python bench.py --steps 5 --warmup 3 --series 96 --no-cpu 2>&1 | python tools/benchline.py
