@@ -62,6 +62,9 @@ struct Engine {
     WaveCtl *d_ctl = nullptr, *h_ctl = nullptr;
     FrameWork *d_frames = nullptr, *h_frames = nullptr;
     size_t frames_cap = 0;
+    ChunkRef *d_chunks = nullptr, *h_chunks = nullptr;  // stats work items (stats.cuh)
+    StatsPart *d_parts = nullptr;
+    size_t chunks_cap = 0, parts_cap = 0;
     double *d_samples = nullptr;
     size_t samples_cap = 0;
     FftEntry *d_arena = nullptr;
@@ -389,10 +392,10 @@ void device_free(Device &D) {
         void *ptrs[] = {P.rle_k0, P.rle_k1, P.rle_i0, P.rle_i1, P.rle_bnd, P.fft_W, P.fft_Xd, P.fft_keys, P.fft_rank,
                         P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.poly_slope, P.dec_pts,
                         P.dec_mark, P.dec_idx, E.queues, E.d_ctl, E.d_frames, E.d_samples, E.d_arena, E.d_payload,
-                        E.d_dec, E.d_pay_in, E.d_out, E.d_status, E.d_spec_xd, E.d_spec_keys};
+                        E.d_dec, E.d_pay_in, E.d_out, E.d_status, E.d_spec_xd, E.d_spec_keys, E.d_chunks, E.d_parts};
         for (void *p : ptrs)
             if (p) cudaFree(p);
-        void *hp[] = {E.h_ctl, E.h_frames, E.h_dec, E.h_status};
+        void *hp[] = {E.h_ctl, E.h_frames, E.h_dec, E.h_status, E.h_chunks};
         for (void *p : hp)
             if (p) cudaFreeHost(p);
         for (auto &ev : E.ev)
@@ -427,6 +430,13 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     if ((rc = grow(D, E.st, E.h_frames, hcap, E.frames_cap, true))) return rc;
     uint64_t arena = 0, spec = 0, samples = 0;
     bool any_noop = false;
+    size_t n_chunks = 0;
+    for (uint32_t i = 0; i < n; i++) n_chunks += (reqs[i].len + STATS_CHUNK - 1) / STATS_CHUNK;
+    hcap = E.chunks_cap;
+    if ((rc = grow(D, E.st, E.d_chunks, E.chunks_cap, n_chunks))) return rc;
+    if ((rc = grow(D, E.st, E.h_chunks, hcap, E.chunks_cap, true))) return rc;
+    if ((rc = grow(D, E.st, E.d_parts, E.parts_cap, n_chunks))) return rc;
+    uint32_t nc = 0;
     for (uint32_t i = 0; i < n; i++) {
         FrameWork &f = E.h_frames[i];
         memset(&f, 0, sizeof f);
@@ -439,6 +449,8 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
         f.forced = r.forced;
         f.geom = -1;
         f.spec_off = ~0ull;
+        f.chunk0 = nc;
+        for (uint32_t c0 = 0; c0 < r.len; c0 += STATS_CHUNK) E.h_chunks[nc++] = ChunkRef{i, c0};
         samples += r.len;
         uint8_t eff = (r.comp == C_AUTO && r.forced != 0xFF) ? r.forced : r.comp;
         any_noop |= r.comp == C_NOOP;
@@ -473,12 +485,13 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     if ((rc = grow(D, E.st, E.d_payload, E.payload_cap, (size_t)std::max<uint64_t>(samples, 1u << 20) + 64 * (size_t)n))) return rc;
     cudaStream_t st = E.st;
     CK(cudaMemcpyAsync(E.d_frames, E.h_frames, (size_t)n * sizeof(FrameWork), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(E.d_chunks, E.h_chunks, n_chunks * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(E.queues, 0, 64 * sizeof(unsigned), st));
     CK(cudaMemsetAsync(E.d_ctl, 0, sizeof(WaveCtl), st));
     CK(cudaEventRecord(E.ev[0], st));
-    launch_stats(E.d_frames, n, d_samples, E.queues + 0, st);
+    launch_stats(E.d_frames, E.d_chunks, (uint32_t)n_chunks, d_samples, E.d_parts, E.queues + 0, st);
     CK(cudaEventRecord(E.ev[1], st));
-    launch_plan(E.d_frames, n, st);
+    launch_plan(E.d_frames, n, d_samples, E.d_parts, st);
     launch_poly(E.d_frames, n, d_samples, max_err, D.inv_d2, E.pool, E.queues + 1, st);
     CK(cudaEventRecord(E.ev[2], st));
     launch_rle(E.d_frames, n, d_samples, max_err, E.pool, E.queues + 2, st);

@@ -52,6 +52,8 @@ struct FrameWork {
     int32_t geom;        // index into the FftGeom table, -1 = direct DFT (N < 128)
     uint32_t aux_size;   // Noop / Constant payload size
     uint32_t fwd_done;   // k_fft_fwd left the half spectrum + keys at spec_off
+    uint32_t chunk0;     // first entry of this frame in the wave's stats chunk table
+    uint32_t pad3;
     uint64_t spec_off;   // entry offset into the wave's spectrum arena (~0 = frame not eligible for fft2.cuh)
     // ---- result
     uint8_t winner, near_tie;

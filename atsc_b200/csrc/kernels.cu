@@ -39,23 +39,27 @@ __device__ inline FftWs fft_slot(const SlotPool &p, int s) {
 // =========================================================================================
 // stats
 // =========================================================================================
-__global__ void __launch_bounds__(BLOCK, 2) k_stats(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
-                                                 unsigned *q) {
+__global__ void __launch_bounds__(BLOCK, 2) k_stats(const FrameWork *__restrict__ fr, const ChunkRef *__restrict__ chunks,
+                                                    uint32_t n_chunks, const double *__restrict__ samples,
+                                                    StatsPart *parts, unsigned *q) {
     __shared__ StatsSmem sm;
     __shared__ int s_item;
     for (;;) {
-        int i = queue_next(q, &s_item);
-        if (i >= (int)n) break;
-        FrameWork *fw = &fr[i];
-        frame_stats(samples + fw->off, fw->len, fw, &sm);
+        int c = queue_next(q, &s_item);
+        if (c >= (int)n_chunks) break;
+        const ChunkRef ch = chunks[c];
+        const FrameWork *fw = &fr[ch.frame];
+        chunk_stats(samples + fw->off, fw->len, ch.start, min(ch.start + STATS_CHUNK, fw->len), parts + c, &sm);
     }
 }
 
-// which candidates run for each frame (frame/mod.rs:71-149, compressor/mod.rs:63-107)
-__global__ void k_plan(FrameWork *fr, uint32_t n) {
+// per frame: combine the chunk partials into the stats, then decide which candidates run
+// (frame/mod.rs:71-149, compressor/mod.rs:63-107)
+__global__ void k_plan(FrameWork *fr, uint32_t n, const double *__restrict__ samples, const StatsPart *__restrict__ parts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     FrameWork *fw = &fr[i];
+    finish_stats(samples + fw->off, fw->len, parts + fw->chunk0, (fw->len + STATS_CHUNK - 1) / STATS_CHUNK, fw);
     uint8_t np = 0, nr = 0, nf = 0, pt = 0;
     switch (fw->comp) {
         case C_AUTO:
@@ -1073,10 +1077,13 @@ int kernels_init() {
 
 static inline int grid_for(uint32_t n, int slots) { return (int)(n < (uint32_t)slots ? n : (uint32_t)slots); }
 
-void launch_stats(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st) {
-    k_stats<<<grid_for(n, 2 * sms()), BLOCK, 0, st>>>(fr, n, samples, q);
+void launch_stats(const FrameWork *fr, const ChunkRef *chunks, uint32_t n_chunks, const double *samples, StatsPart *parts,
+                  unsigned *q, cudaStream_t st) {
+    k_stats<<<grid_for(n_chunks, 2 * sms()), BLOCK, 0, st>>>(fr, chunks, n_chunks, samples, parts, q);
 }
-void launch_plan(FrameWork *fr, uint32_t n, cudaStream_t st) { k_plan<<<(n + 255) / 256, 256, 0, st>>>(fr, n); }
+void launch_plan(FrameWork *fr, uint32_t n, const double *samples, const StatsPart *parts, cudaStream_t st) {
+    k_plan<<<(n + 63) / 64, 64, 0, st>>>(fr, n, samples, parts);
+}
 void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_err, const double *inv_d2,
                  SlotPool pool, unsigned *q, cudaStream_t st) {
     k_poly<<<grid_for(n, pool.poly_slots), BLOCK, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "fft.cuh"
 #include "rle.cuh"
+#include "stats.cuh"
 
 namespace atsc {
 
@@ -42,8 +43,9 @@ struct DecFrame {
 };
 
 // compress pipeline; q = device array of >= 8 zeroed uint32 work-queue counters
-void launch_stats(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st);
-void launch_plan(FrameWork *fr, uint32_t n, cudaStream_t st);
+void launch_stats(const FrameWork *fr, const ChunkRef *chunks, uint32_t n_chunks, const double *samples, StatsPart *parts,
+                  unsigned *q, cudaStream_t st);
+void launch_plan(FrameWork *fr, uint32_t n, const double *samples, const StatsPart *parts, cudaStream_t st);
 void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_err, const double *inv_d2,
                  SlotPool pool, unsigned *q, cudaStream_t st);
 void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err, SlotPool pool,

@@ -7,8 +7,7 @@ namespace atsc {
 
 struct StatsSmem {
     double mn[32], mx[32];
-    uint32_t flags[32], runs[32], idxb[32];
-    uint32_t first_zero;
+    uint32_t flags[32], runs[32], idxb[32], e64k[32];
 };
 
 // `fractional` of split_n (optimizer/utils.rs:115-160) without building the integer part.
@@ -32,121 +31,221 @@ __device__ inline bool frac_nonzero(double x) {
     return f;
 }
 
-// Computes the frame's stats into fw (all threads must call; result written by thread 0).
-// min / max follow the reference exactly: start from data[0], strict comparisons in index order
-// (NaN never wins).  Equal values have equal bits except +0.0 / -0.0, so "first occurrence" only
-// matters when an extreme is zero and both signs are present: that case takes a second pass.
-__device__ inline void frame_stats(const double *__restrict__ d, uint32_t N, FrameWork *fw,
-                                   StatsSmem *sm) {
-    const double first = d[0];
-    double mn = first, mx = first;
-    uint32_t flags = 0;  // bit0 fractional, bit1 saw -0.0
-    uint32_t runs = 0, idxb = 0;
-    const uint32_t T = blockDim.x;
-    const int ln = threadIdx.x & 31;
-    constexpr int U = 4;  // independent coalesced loads in flight per thread
-    for (uint32_t i0 = 0; i0 < N; i0 += U * T) {
-        double v[U], nx[U];
-        const uint32_t base = i0 + threadIdx.x;
-        if (i0 + U * T <= N) {
-#pragma unroll
-            for (int u = 0; u < U; u++) v[u] = d[base + u * T];
-        } else {
-#pragma unroll
-            for (int u = 0; u < U; u++) v[u] = base + u * T < N ? d[base + u * T] : 0.0;
+// per-sample accumulators of one thread
+struct StatsAcc {
+    double mn, mx;
+    uint32_t flags;  // bit0 fractional, bit1 saw -0.0, bit2 saw 0 < |x| < 2^-64 (fractional needs the exact test)
+    uint32_t ends, ends251, ends64k;  // run ends before the last sample: all / at i+1 >= 251 / at i+1 >= 65536
+};
+
+// sample with value val, right-hand neighbour nx and index i1 - 1.
+// UNIFORM: every index of the chunk is on the same side of the varint thresholds (the caller
+// scales `ends`); RUNS = false: value part only.
+template <bool UNIFORM, bool RUNS = true>
+__device__ __forceinline__ void stats_sample(StatsAcc &a, double val, double nx, uint32_t i1) {
+    const int hi = __double2hiint(val), lo = __double2loint(val);
+    if (!(a.flags & 1u)) {
+        // fractional (split_n): for 2^-64 <= |x| < 2^52 exactly "x has a fractional part"; NaN / inf /
+        // integers >= 2^52 / zero: no; the sliver 0 < |x| < 2^-64 is settled by finish_stats
+        const bool ne = val != trunc(val);
+        const uint32_t ef = (uint32_t)hi & 0x7FF00000u;
+        if (ne && (ef - 0x3BF00000u) < 0x44000000u) a.flags |= 1u;
+        if (ne && ef < 0x3BF00000u) a.flags |= 4u;
+    }
+    if (lo == 0 && hi == (int)0x80000000) a.flags |= 2u;
+    // strict comparisons: NaN never wins (optimizer/utils.rs:57-64); the sign of a zero extreme is
+    // settled afterwards (finish_stats)
+    if (val < a.mn) a.mn = val;
+    if (val > a.mx) a.mx = val;
+    // rle.rs:154: a run ends where the next value differs
+    if (RUNS && nx != val) {
+        a.ends++;
+        if (!UNIFORM) {
+            a.ends251 += (i1 >= 251u) ? 1u : 0u;
+            a.ends64k += (i1 >= 65536u) ? 1u : 0u;
         }
-        // the right-hand neighbour comes from a warp shuffle (only lane 31 touches memory again)
+    }
+}
+
+// One work item of k_stats: samples [start, start + STATS_CHUNK) of a frame.  Frames are cut into
+// chunks so the pass balances over the SMs no matter how few frames a wave has.
+constexpr uint32_t STATS_CHUNK = 32768;
+struct ChunkRef {
+    uint32_t frame, start;
+};
+struct StatsPart {
+    double mn, mx;  // +inf / -inf when the chunk holds no comparable value
+    uint32_t flags, ends, ends251, ends64k;
+};
+
+template <bool UNIFORM>
+__device__ __forceinline__ void chunk_scan(StatsAcc &a, const double *__restrict__ dc, uint32_t n, uint32_t c0) {
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    const int ln = t & 31;
+    const bool vec = (((uintptr_t)dc >> 3) & 1u) == 0u;  // 16-byte aligned chunk: two samples per load
+    if (vec) {
+        constexpr uint32_t U = 2;
+        const double2 *d2 = reinterpret_cast<const double2 *>(dc);
+        const uint32_t P = n / 2;  // pairs whose second element still has a neighbour
+        const uint32_t Pfull = P - P % (U * T);
+        uint32_t p0 = 0;
+        for (; p0 < Pfull; p0 += U * T) {  // every pair of the tile exists and has a successor pair or dc[2P]
+            double2 v[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            nx[u] = __shfl_down_sync(0xffffffffu, v[u], 1);
-            if (ln == 31 && base + u * T + 1 < N) nx[u] = d[base + u * T + 1];
+            for (uint32_t u = 0; u < U; u++) v[u] = __ldg(d2 + p0 + u * T + t);
+#pragma unroll
+            for (uint32_t u = 0; u < U; u++) {
+                const uint32_t p = p0 + u * T + t;
+                double nx = __shfl_down_sync(0xffffffffu, v[u].x, 1);
+                if (ln == 31) nx = dc[2 * p + 2];
+                stats_sample<UNIFORM>(a, v[u].x, v[u].y, c0 + 2 * p + 1);
+                stats_sample<UNIFORM>(a, v[u].y, nx, c0 + 2 * p + 2);
+            }
         }
+        for (; p0 < P; p0 += T) {
+            const uint32_t p = p0 + t;
+            const double2 v = p < P ? __ldg(d2 + p) : make_double2(0.0, 0.0);
+            double nx = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if ((ln == 31 || p + 1 >= P) && p < P) nx = dc[2 * p + 2];
+            if (p < P) {
+                stats_sample<UNIFORM>(a, v.x, v.y, c0 + 2 * p + 1);
+                stats_sample<UNIFORM>(a, v.y, nx, c0 + 2 * p + 2);
+            }
+        }
+        for (uint32_t i = 2 * P + t; i < n; i += T) stats_sample<UNIFORM>(a, dc[i], dc[i + 1], c0 + i + 1);  // <= 1 leftover
+    } else {
+        constexpr uint32_t U = 4;
+        for (uint32_t i0 = 0; i0 < n; i0 += U * T) {
+            double v[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i = base + u * T;
-            if (i >= N) continue;
-            const double val = v[u];
-            flags |= frac_nonzero(val) ? 1u : 0u;
-            if (__double_as_longlong(val) == (long long)0x8000000000000000ull) flags |= 2u;
-            if (val < mn) mn = val;
-            if (val > mx) mx = val;
-            // rle.rs:154: run ends where the next value differs (or at the end)
-            const bool last = i + 1 >= N;
-            if (last || nx[u] != val) {
-                runs++;
-                if (!last) idxb += 1u + ((i + 1 >= 251u) ? 2u : 0u) + ((i + 1 >= 65536u) ? 2u : 0u);  // varint_len(i + 1)
+            for (uint32_t u = 0; u < U; u++) v[u] = (i0 + u * T + t < n) ? dc[i0 + u * T + t] : 0.0;
+#pragma unroll
+            for (uint32_t u = 0; u < U; u++) {
+                const uint32_t i = i0 + u * T + t;
+                double nx = __shfl_down_sync(0xffffffffu, v[u], 1);
+                if ((ln == 31 || i + 1 >= n) && i < n) nx = dc[i + 1];
+                if (i < n) stats_sample<UNIFORM>(a, v[u], nx, c0 + i + 1);
             }
         }
     }
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+}
+
+// Partial stats of samples [c0, c1) of a frame of N samples (all threads call; thread 0 writes *out).
+__device__ inline void chunk_stats(const double *__restrict__ d, uint32_t N, uint32_t c0, uint32_t c1, StatsPart *out,
+                                   StatsSmem *sm) {
+    StatsAcc a;
+    a.mn = __longlong_as_double(0x7FF0000000000000ll);
+    a.mx = -a.mn;
+    a.flags = a.ends = a.ends251 = a.ends64k = 0;
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    // samples [c0, e) have a right-hand neighbour inside the frame; a frame's last sample is value-only
+    const uint32_t e = min(c1, N - 1);
+    // varint_len(i + 1) of the run ends is the same for the whole chunk unless it straddles 251 / 65536
+    const bool hi = c0 + 1 >= 65536u, mid = c0 + 1 >= 251u && e < 65536u, lo = e < 251u;
+    if (hi || mid || lo)
+        chunk_scan<true>(a, d + c0, e - c0, c0);
+    else
+        chunk_scan<false>(a, d + c0, e - c0, c0);
+    if (t == 0 && c1 == N) stats_sample<true, false>(a, d[N - 1], 0.0, 0);  // the frame's last sample
+    uint32_t idx3[3] = {a.ends, (hi || mid) ? a.ends : a.ends251, hi ? a.ends : a.ends64k};
+    const int lane = t & 31, w = t >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        double a = __shfl_down_sync(0xffffffffu, mn, o), b = __shfl_down_sync(0xffffffffu, mx, o);
-        if (a < mn) mn = a;
-        if (b > mx) mx = b;
-        flags |= __shfl_down_sync(0xffffffffu, flags, o);
-        runs += __shfl_down_sync(0xffffffffu, runs, o);
-        idxb += __shfl_down_sync(0xffffffffu, idxb, o);
+        a.mn = fmin(a.mn, __shfl_down_sync(0xffffffffu, a.mn, o));
+        a.mx = fmax(a.mx, __shfl_down_sync(0xffffffffu, a.mx, o));
+        a.flags |= __shfl_down_sync(0xffffffffu, a.flags, o);
+#pragma unroll
+        for (int k = 0; k < 3; k++) idx3[k] += __shfl_down_sync(0xffffffffu, idx3[k], o);
     }
     __syncthreads();
     if (lane == 0) {
-        sm->mn[w] = mn;
-        sm->mx[w] = mx;
-        sm->flags[w] = flags;
-        sm->runs[w] = runs;
-        sm->idxb[w] = idxb;
+        sm->mn[w] = a.mn;
+        sm->mx[w] = a.mx;
+        sm->flags[w] = a.flags;
+        sm->runs[w] = idx3[0];
+        sm->idxb[w] = idx3[1];
+        sm->e64k[w] = idx3[2];
     }
-    if (threadIdx.x == 0) sm->first_zero = 0xFFFFFFFFu;
     __syncthreads();
-    {
-        int nw = blockDim.x >> 5;
-        for (int k = 0; k < nw; k++) {
-            double a = sm->mn[k], b = sm->mx[k];
-            if (a < mn) mn = a;
-            if (b > mx) mx = b;
-            flags |= sm->flags[k];
+    if (w == 0) {
+        const int nw = T >> 5;
+        double mn = lane < nw ? sm->mn[lane] : a.mn, mx = lane < nw ? sm->mx[lane] : a.mx;
+        uint32_t fl = lane < nw ? sm->flags[lane] : 0u;
+        uint32_t r0 = lane < nw ? sm->runs[lane] : 0u, r1 = lane < nw ? sm->idxb[lane] : 0u, r2 = lane < nw ? sm->e64k[lane] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+            fl |= __shfl_down_sync(0xffffffffu, fl, o);
+            r0 += __shfl_down_sync(0xffffffffu, r0, o);
+            r1 += __shfl_down_sync(0xffffffffu, r1, o);
+            r2 += __shfl_down_sync(0xffffffffu, r2, o);
+        }
+        if (lane == 0) {
+            StatsPart p;
+            p.mn = mn;
+            p.mx = mx;
+            p.flags = fl;
+            p.ends = r0;
+            p.ends251 = r1;
+            p.ends64k = r2;
+            *out = p;
         }
     }
-    // every thread now holds the frame's min / max / flags
+}
+
+// Combines a frame's chunk partials into DataStats (optimizer/utils.rs:39-89) + the run counts
+// (rle.rs:142-189); one thread per frame.  min / max follow the reference exactly: start from
+// data[0], strict comparisons in index order (NaN never wins).  Equal values have equal bits except
+// +0.0 / -0.0, so "first occurrence" only matters when an extreme is zero and a -0.0 exists: that
+// (rare) case scans for the first zero.
+__device__ inline void finish_stats(const double *__restrict__ d, uint32_t N, const StatsPart *parts, uint32_t nparts,
+                                    FrameWork *fw) {
+    const double first = d[0];
+    double mn = first, mx = first;
+    uint32_t flags = 0, runs = 1, idxb = 0;  // runs: + the run that ends with the last sample
+    for (uint32_t k = 0; k < nparts; k++) {
+        const StatsPart p = parts[k];
+        if (p.mn < mn) mn = p.mn;
+        if (p.mx > mx) mx = p.mx;
+        flags |= p.flags;
+        runs += p.ends;
+        idxb += p.ends + 2u * p.ends251 + 2u * p.ends64k;
+    }
+    if ((flags & 5u) == 4u) {
+        // no ordinary fractional value, but values below 2^-64 exist: the exact restatement decides (rare)
+        for (uint32_t x = 0; x < N && !(flags & 1u); x++) {
+            bool f;
+            (void)split_n(d[x], &f);
+            if (f) flags |= 1u;
+        }
+    }
     double vmin = mn, vmax = mx;
     if (first != first) {
         vmin = vmax = first;  // min = max = data[0] = NaN and no comparison ever replaces it
     } else if ((flags & 2u) && (vmin == 0.0 || vmax == 0.0)) {
         // a -0.0 exists and an extreme is zero: its sign is that of the first zero in the frame
-        uint32_t fz = 0xFFFFFFFFu;
-        for (uint32_t x = threadIdx.x; x < N; x += T)
+        double z = 0.0;
+        for (uint32_t x = 0; x < N; x++)
             if (d[x] == 0.0) {
-                fz = x;
+                z = d[x];
                 break;
             }
-        if (fz != 0xFFFFFFFFu) atomicMin(&sm->first_zero, fz);
-        __syncthreads();
-        const double z = d[sm->first_zero];
         if (vmin == 0.0) vmin = z;
         if (vmax == 0.0) vmax = z;
     }
-    if (threadIdx.x == 0) {
-        int nw = blockDim.x >> 5;
-        runs = 0;
-        idxb = 0;
-        for (int k = 0; k < nw; k++) {
-            runs += sm->runs[k];
-            idxb += sm->idxb[k];
-        }
-        bool f;
-        int64_t max_int = split_n(vmax, &f);
-        int64_t min_int = split_n(vmin, &f);
-        const bool frac = (flags & 1u) != 0;
-        fw->vmin = vmin;
-        fw->vmax = vmax;
-        fw->fractional = frac ? 1 : 0;
-        fw->bitdepth = frac ? BD_F64 : (uint8_t)bitdepth_of(max_int, min_int);
-        fw->is_const = (vmin == vmax) ? 1 : 0;
-        fw->f32_const = ((float)vmax == (float)vmin) ? 1 : 0;
-        fw->n_runs = runs;
-        fw->rle_idx_bytes = idxb + 1;  // + varint_len(0) for the first run
-    }
-    __syncthreads();
+    bool f;
+    int64_t max_int = split_n(vmax, &f);
+    int64_t min_int = split_n(vmin, &f);
+    const bool frac = (flags & 1u) != 0;
+    fw->vmin = vmin;
+    fw->vmax = vmax;
+    fw->fractional = frac ? 1 : 0;
+    fw->bitdepth = frac ? BD_F64 : (uint8_t)bitdepth_of(max_int, min_int);
+    fw->is_const = (vmin == vmax) ? 1 : 0;
+    fw->f32_const = ((float)vmax == (float)vmin) ? 1 : 0;
+    fw->n_runs = runs;
+    fw->rle_idx_bytes = idxb + 1;  // + varint_len(0) for the first run
 }
 
 }  // namespace atsc
