@@ -321,6 +321,113 @@ __device__ inline uint32_t f2_pass2(int M1, const float2 *__restrict__ tw2, cons
     return nz;
 }
 
+// ---------------------------------------------------------------------------------------
+// PROBE: the same transform restricted to the 2*RB rows k1 = 1 + RA*u and their partners
+// M1 - k1 = (RA-1) + RA*(RB-1-u) (u < RB), i.e. 2*RB*243 of the M bins, bit-identical to what the
+// full transform computes for them.  Used to prove "at least c nonzero bins" (Auto pruning) at
+// roughly a third of the full cost: pass-1 stage 2 runs for q in {1, RA-1} only, pass 2 for 2*RB
+// rows only, and the intermediate is 1/8 of W:  Wp[n2 * 2RB + lr],  lr < RB <-> k1 = 1 + RA*lr,
+// lr >= RB <-> k1 = M1 - (1 + RA*(lr - RB)).
+// ---------------------------------------------------------------------------------------
+template <int RA, int RB>
+__device__ inline void f2_probe_pass1(const double *__restrict__ d, int N, int prefix, const float2 *__restrict__ tw1,
+                                      const float2 *__restrict__ T4, float2 *Wp, float2 *sm) {
+    static_assert(RA >= 4, "probe needs two distinct output families");
+    constexpr int M1 = RA * RB, P1 = 2 * RB + 1;  // only y[q + RA*t] for the two q is kept: [lc][2][RB]
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const bool vec = (((uintptr_t)d >> 3) & 1u) == ((uint32_t)prefix & 1u);
+    for (int c0 = 0; c0 < F2_M2; c0 += F2_TC) {
+        const int nb = min(F2_TC, F2_M2 - c0);
+        for (int item = tid; item < RB * F2_TC; item += nth) {
+            const int lc = item & (F2_TC - 1), p = item / F2_TC;
+            if (lc >= nb) continue;
+            float2 a[RA];
+#pragma unroll
+            for (int t = 0; t < RA; t++) a[t] = f2_load_z(d, N, prefix, (p + RB * t) * F2_M2 + c0 + lc, vec);
+            DftS<RA, 1, false>::run(a);  // only outputs 1 and RA-1 are used: the rest is dead code
+            float2 *y = sm + lc * P1;
+            y[p] = cmul(a[1], __ldg(tw1 + p));
+            y[RB + p] = cmul(a[RA - 1], __ldg(tw1 + p * (RA - 1)));
+        }
+        __syncthreads();
+        if (c0 + F2_TC < F2_M2) {
+            for (int i = tid; i < M1 * 4; i += nth) {
+                const int e = i >> 2, ln = i & 3;
+                int ix = 2 * (e * F2_M2 + c0 + F2_TC) - prefix + 16 * ln;
+                ix = min(max(ix, 0), N - 1);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(d + ix));
+            }
+        }
+        for (int item = tid; item < 2 * F2_TC; item += nth) {
+            const int fam = item & 1, lc = item >> 1;  // fam 0: q = 1, fam 1: q = RA-1
+            if (lc >= nb) continue;
+            float2 b[RB];
+            const float2 *y = sm + lc * P1 + fam * RB;
+#pragma unroll
+            for (int t = 0; t < RB; t++) b[t] = y[t];
+            DftS<RB, 1, false>::run(b);
+            const int c = c0 + lc, q = fam ? RA - 1 : 1;
+#pragma unroll
+            for (int u = 0; u < RB; u++) {
+                const int k1 = q + RA * u, lr = fam ? RB + (RB - 1 - u) : u;
+                __stcg(Wp + c * (2 * RB) + lr, cmul(b[u], __ldg(T4 + c * M1 + k1)));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// count of nonzero bins among the probed rows (this thread's share)
+__device__ inline uint32_t f2_probe_pass2(int M1, int RA, const float2 *__restrict__ tw2, const float2 *__restrict__ twL1,
+                                          const float2 *__restrict__ twL2, const float2 *Wp, float2 *sm) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int RB = M1 / RA, npairs = RB, stride = 2 * RB;
+    uint32_t nz = 0;
+    for (int pr0 = 0; pr0 < npairs; pr0 += F2_PAIRS) {
+        const int np = min(F2_PAIRS, npairs - pr0);
+        for (int item = tid; item < 9 * 2 * F2_PAIRS; item += nth) {
+            const int lr = item & (2 * F2_PAIRS - 1), p = item / (2 * F2_PAIRS), l = lr & (F2_PAIRS - 1);
+            if (l >= np) continue;
+            const int wl = lr < F2_PAIRS ? pr0 + l : RB + pr0 + l;  // compact row index in Wp
+            float2 a[27];
+#pragma unroll
+            for (int t = 0; t < 27; t++) a[t] = __ldcg(Wp + (p + 9 * t) * stride + wl);
+            DftS<27, 1, false>::run(a);
+            float2 *y = sm + lr * F2_M2 + 27 * p;
+            y[0] = a[0];
+#pragma unroll
+            for (int q = 1; q < 27; q++) y[q] = cmul(a[q], __ldg(tw2 + p * q));
+        }
+        __syncthreads();
+        for (int item = tid; item < F2_PAIRS * 27; item += nth) {
+            const int q = item % 27, pl = item / 27;
+            if (pl >= np) continue;
+            float2 A[9], B[9];
+            const float2 *ya = sm + pl * F2_M2 + q, *yb = sm + (pl + F2_PAIRS) * F2_M2 + (26 - q);
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                A[t] = ya[27 * t];
+                B[t] = yb[27 * t];
+            }
+            DftS<9, 1, false>::run(A);
+            DftS<9, 1, false>::run(B);
+            const int k1 = 1 + RA * (pr0 + pl);
+            const float2 w1 = __ldg(twL1 + k1);
+#pragma unroll
+            for (int u = 0; u < 9; u++) {
+                const int k2 = q + 27 * u;
+                const float2 w = cmul(w1, __ldg(twL2 + k2));
+                const float2 Xk = f2_post(A[u], B[8 - u], w);
+                const float2 Xm = f2_post(B[8 - u], A[u], make_float2(-w.x, w.y));
+                nz += (Xk.x != 0.f || Xk.y != 0.f) ? 1u : 0u;
+                nz += (Xm.x != 0.f || Xm.y != 0.f) ? 1u : 0u;
+            }
+        }
+        __syncthreads();
+    }
+    return nz;
+}
+
 __device__ inline bool f2_supported(const FftGeom &g) {
     return g.real && g.M2 == (uint32_t)F2_M2 && g.T4 != nullptr &&
            (g.M1 == 288u || g.M1 == 144u || g.M1 == 72u || g.M1 == 36u || g.M1 == 18u);
@@ -335,6 +442,20 @@ __device__ inline void f2_forward_pass1(const double *__restrict__ d, int N, int
         case 36: f2_pass1<4, 9>(d, N, prefix, g.tw1, g.T4, W, sm); break;
         default: f2_pass1<2, 9>(d, N, prefix, g.tw1, g.T4, W, sm); break;
     }
+}
+
+// probe (see above): this thread's count of nonzero bins among 2*RB*243 probed ones; 0 when the
+// geometry has no probe (M1 = 18)
+__device__ inline uint32_t f2_probe(const double *__restrict__ d, int N, int prefix, const FftGeom &g, float2 *W, float2 *sm) {
+    int RA;
+    switch (g.M1) {
+        case 288: f2_probe_pass1<16, 18>(d, N, prefix, g.tw1, g.T4, W, sm); RA = 16; break;
+        case 144: f2_probe_pass1<16, 9>(d, N, prefix, g.tw1, g.T4, W, sm); RA = 16; break;
+        case 72: f2_probe_pass1<8, 9>(d, N, prefix, g.tw1, g.T4, W, sm); RA = 8; break;
+        case 36: f2_probe_pass1<4, 9>(d, N, prefix, g.tw1, g.T4, W, sm); RA = 4; break;
+        default: return 0u;
+    }
+    return f2_probe_pass2((int)g.M1, RA, g.tw2, g.twL1, g.twL2, W, sm);
 }
 
 }  // namespace atsc

@@ -404,7 +404,6 @@ __global__ void __launch_bounds__(F2_THREADS, 2) k_fft_fwd(FrameWork *fr, uint32
         const uint32_t N = fw->len;
         const bool bounded = fw->bounded != 0;
         const uint32_t prefix = (bounded && N >= 128) ? (sg.L - N) / 2 : 0u;
-        f2_forward_pass1(samples + fw->off, (int)N, (int)prefix, sg, W, dyn_f2);
         float2 *Xd = spec_xd + fw->spec_off;
         uint32_t *keys = spec_keys + fw->spec_off;
         // a later candidate can only lose to FFT on size; FFT wins ties (frame/mod.rs:77,104,141)
@@ -414,13 +413,24 @@ __global__ void __launch_bounds__(F2_THREADS, 2) k_fft_fwd(FrameWork *fr, uint32
             if (fw->rle_valid == 1) bound = min(bound, fw->rle_size);
         }
         if (bound != 0xFFFFFFFFu) {
-            // count-only second pass: the first schedule point keeps c1 = min(max_freq, #nonzero bins)
-            // entries (fft.rs:249-252) and at most `smax` of them have a one-byte position
-            const uint32_t nz = block_sum_u32(f2_pass2<false>((int)sg.M1, sg.tw2, sg.twL1, sg.twL2, W, dyn_f2, Xd, keys), sh);
+            // The first schedule point keeps c1 = min(max_freq, #nonzero bins) entries (fft.rs:249-252),
+            // at most `smax` of them with a one-byte position, and the payload only grows from there.
+            // A probe of 1/8 of the spectrum (bit-identical to the full transform on those bins) usually
+            // finds enough nonzero bins to prove that even this first point is larger than the bound.
             const uint32_t mf = (3 >= N / 100) ? 3 : N / 100;
-            const uint32_t c1 = min(min(mf, nz), min(fw->fft_list_cap, (uint32_t)FFT_KCAP));
+            const uint32_t cap = min(fw->fft_list_cap, (uint32_t)FFT_KCAP);
             const uint32_t smax = sg.Bn > 65536u ? 502u : 251u;
-            if (fft_payload_size(c1, min(c1, smax)) > bound) {
+            uint32_t nz = block_sum_u32(f2_probe(samples + fw->off, (int)N, (int)prefix, sg, W, dyn_f2), sh);
+            uint32_t c1 = min(min(mf, nz), cap);
+            bool pruned = fft_payload_size(c1, min(c1, smax)) > bound;
+            if (!pruned) {
+                // sparse spectrum (or no probe for this length): count every bin
+                f2_forward_pass1(samples + fw->off, (int)N, (int)prefix, sg, W, dyn_f2);
+                nz = block_sum_u32(f2_pass2<false>((int)sg.M1, sg.tw2, sg.twL1, sg.twL2, W, dyn_f2, Xd, keys), sh);
+                c1 = min(min(mf, nz), cap);
+                pruned = fft_payload_size(c1, min(c1, smax)) > bound;
+            }
+            if (pruned) {
                 if (t == 0) {
                     fw->fft_count = c1;
                     fw->fft_err = max_err + 1.0;
@@ -431,6 +441,8 @@ __global__ void __launch_bounds__(F2_THREADS, 2) k_fft_fwd(FrameWork *fr, uint32
                 }
                 continue;
             }
+        } else {
+            f2_forward_pass1(samples + fw->off, (int)N, (int)prefix, sg, W, dyn_f2);
         }
         (void)f2_pass2<true>((int)sg.M1, sg.tw2, sg.twL1, sg.twL2, W, dyn_f2, Xd, keys);
         if (t == 0) fw->fwd_done = 1;
