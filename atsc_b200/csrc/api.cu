@@ -429,7 +429,8 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     if ((rc = grow(D, E.st, E.d_frames, E.frames_cap, n))) return rc;
     if ((rc = grow(D, E.st, E.h_frames, hcap, E.frames_cap, true))) return rc;
     uint64_t arena = 0, spec = 0, samples = 0;
-    bool any_noop = false;
+    bool any_noop = false, any_small = false, any_large = false;
+    uint32_t small_lmax = 2;
     size_t n_chunks = 0;
     for (uint32_t i = 0; i < n; i++) n_chunks += (reqs[i].len + STATS_CHUNK - 1) / STATS_CHUNK;
     hcap = E.chunks_cap;
@@ -456,6 +457,10 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
         any_noop |= r.comp == C_NOOP;
         if (eff == C_FFT || eff == C_AUTO) {
             uint32_t L = (r.bounded && r.len >= 128) ? padded_len(D, r.len) : r.len;
+            f.fft_small = L <= 1152;
+            any_small |= L <= 1152;
+            if (L <= 1152) small_lmax = std::max(small_lmax, L);
+            any_large |= L > 1152;
             if (r.len >= 128) {
                 int gi;
                 if ((rc = get_geom(D, L, &gi))) {
@@ -496,13 +501,20 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     CK(cudaEventRecord(E.ev[2], st));
     launch_rle(E.d_frames, n, d_samples, max_err, E.pool, E.queues + 2, st);
     CK(cudaEventRecord(E.ev[3], st));
+    if (any_small) {
+        launch_fft_small(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.d_arena, small_lmax, E.queues + 8, st);
+        D.launches++;
+    }
     if (spec) {
         launch_fft_fwd(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_spec_xd, E.d_spec_keys, E.queues + 7, st);
         D.launches++;
     }
-    launch_fft(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_arena, E.d_spec_xd, E.d_spec_keys, E.queues + 3, st);
+    if (any_large) {
+        launch_fft(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_arena, E.d_spec_xd, E.d_spec_keys, E.queues + 3, st);
+        D.launches++;
+    }
     CK(cudaEventRecord(E.ev[4], st));
-    D.launches += 5;
+    D.launches += 4;
     if (any_noop) {
         launch_noop_size(E.d_frames, n, d_samples, E.queues + 4, st);
         D.launches++;

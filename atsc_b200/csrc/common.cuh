@@ -41,7 +41,9 @@ struct FrameWork {
     double poly_err;
     // ---- rle candidate
     uint32_t rle_groups, rle_size;
-    uint8_t rle_valid, pad1[3];
+    uint8_t rle_valid;
+    uint8_t fft_small;  // transform length <= 1152: k_fft_small (fft_small.cuh) runs the FFT candidate
+    uint8_t pad1[2];
     // ---- fft candidate
     uint32_t fft_count, fft_size;
     uint16_t fft_iters;
@@ -220,6 +222,14 @@ __device__ __forceinline__ double rcp_1ulp(double o) {
     e = __fma_rn(-o, y1, 1.0);
     y1 = __fma_rn(y1, e, y1);
     return (y1 == y1 && fabs(y) != __longlong_as_double(0x7FF0000000000000ll) && y != 0.0) ? y1 : y;
+}
+
+// One MAPE term |(out - o) / o| (utils/error.rs:110-113) through the reciprocal w = RN(1/o): within
+// 1 ulp of the true quotient (absorbed by the near-tie tolerance, the error only feeds threshold
+// tests); an exactly reproduced sample gives exactly 0.  A zero sample keeps the reference's
+// semantics: w = inf gives inf (out != 0) or NaN (out == 0), SURVEY H5.
+__device__ __forceinline__ double mape_term(double out, double o) {
+    return fabs(__dmul_rn(__dsub_rn(out, o), rcp_1ulp(o)));
 }
 
 // optimizer/utils.rs:115-160 split_n: (integer part as i64, fraction != 0)

@@ -6,6 +6,7 @@
 // Reference citations are relative to /root/reference/atsc/src/.
 #include "kernels.h"
 #include "fft2.cuh"
+#include "fft_small.cuh"
 #include "poly.cuh"
 #include "stats.cuh"
 #include "varscan.cuh"
@@ -375,9 +376,26 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FrameWork *fr, uint32_t 
         int i = queue_next(q, &s_item);
         if (i >= (int)n) break;
         FrameWork *fw = &fr[i];
-        if (!fw->need_fft || fw->fft_valid == 2) continue;  // 2: k_fft_fwd proved the candidate cannot win
+        if (!fw->need_fft || fw->fft_valid == 2 || fw->fft_small) continue;  // 2: k_fft_fwd proved it cannot win
         fft_frame(samples + fw->off, fw, geoms, ws, arena + fw->fft_list_off, max_err, dyn_f2, shd, &sg, spec_xd,
                   spec_keys);
+    }
+}
+
+// FFT candidate of the short frames (fft_small.cuh)
+__global__ void __launch_bounds__(FS_THREADS) k_fft_small(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
+                                                          double max_err, const FftGeom *__restrict__ geoms,
+                                                          FftEntry *arena, uint32_t lmax, unsigned *q) {
+    extern __shared__ double2 dyn_d2[];
+    const FsSmem carved = fs_carve(reinterpret_cast<unsigned char *>(dyn_d2), lmax);
+    const FsSmem *sm = &carved;
+    __shared__ int s_item;
+    for (;;) {
+        int i = queue_next(q, &s_item);
+        if (i >= (int)n) break;
+        FrameWork *fw = &fr[i];
+        if (!fw->need_fft || !fw->fft_small) continue;
+        fft_small_frame(samples + fw->off, fw, geoms, arena + fw->fft_list_off, max_err, sm);
     }
 }
 
@@ -1081,6 +1099,8 @@ int kernels_init() {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_fft_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fft_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs_smem_bytes(FS_LMAX));
+    if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_rle, cudaFuncAttributeMaxDynamicSharedMemorySize, RLE_HIST_WORDS * 4);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, RLE_HIST_WORDS * 4);
@@ -1108,6 +1128,10 @@ void launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err
                 SlotPool pool, FftEntry *arena, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st) {
     k_fft<<<grid_for(n, pool.fft_slots), FFT_THREADS, FFT_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool, arena,
                                                                            spec_xd, spec_keys, q);
+}
+void launch_fft_small(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
+                      FftEntry *arena, uint32_t lmax, unsigned *q, cudaStream_t st) {
+    k_fft_small<<<grid_for(n, 8 * sms()), FS_THREADS, fs_smem_bytes(lmax), st>>>(fr, n, samples, max_err, geoms, arena, lmax, q);
 }
 void launch_fft_fwd(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
                     SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st) {

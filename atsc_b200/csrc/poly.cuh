@@ -103,14 +103,6 @@ __device__ __forceinline__ double round_and_limit5_fast(double x, double mn, dou
     return out;
 }
 
-// One MAPE term |(out - o) / o| (utils/error.rs:110-113) through the reciprocal w = RN(1/o): within
-// 1 ulp of the true quotient (absorbed by the near-tie tolerance, the error only feeds threshold
-// tests); an exactly reproduced sample gives exactly 0.  A zero sample keeps the reference's
-// semantics: w = inf gives inf (out != 0) or NaN (out == 0), SURVEY H5.
-__device__ __forceinline__ double mape_term(double out, double o) {
-    return fabs(__dmul_rn(__dsub_rn(out, o), rcp_1ulp(o)));
-}
-
 // MAPE (utils/error.rs:104-116) of one candidate step against the frame; block-wide.
 // Catmull-Rom path: identical value arithmetic to poly_eval_at (same operations, same order).
 // Thread t owns one offset j inside the segments (its Hermite basis values stay in registers) and
