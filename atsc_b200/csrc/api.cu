@@ -371,8 +371,8 @@ int device_init(Device &D) {
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, D.id));
     // waves in flight per device and samples per wave (tunable for experiments)
-    D.n_engines = env_int("ATSC_ENGINES", 3, 1, MAX_ENGINES);
-    D.wave_samples = (uint64_t)env_int("ATSC_WAVE_MI", 32, 1, 512) << 20;
+    D.n_engines = env_int("ATSC_ENGINES", 4, 1, MAX_ENGINES);
+    D.wave_samples = (uint64_t)env_int("ATSC_WAVE_MI", 72, 1, 512) << 20;
     for (int e = 0; e < D.n_engines; e++)
         if ((rc = engine_init(D, D.eng[e], sms))) return rc;
     CK(cudaMalloc((void **)&D.geoms_dev, GEOM_CAP * sizeof(FftGeom)));

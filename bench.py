@@ -12,8 +12,8 @@ One "step" = one pass of the hot path over the GPU's whole batch:
   value   : Msamples/s, inputs resident in HBM when the clock starts, payloads + frame
             records copied back to the host inside the timed region.
   e2e     : same call with the samples in pinned HOST memory (H2D inside the timed region).
-  roofline: dominant kernel (k_fft) -- algorithmic bytes = 8 B x samples of the frames it
-            transforms / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+  roofline: dominant kernel (largest summed CUDA-event time) -- algorithmic bytes = 8 B x samples of
+            the frames it reads / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline: the oracle port (C restatement of the reference) on the host cores, bounded sample.
   decompress: GB/s of f64 output for the BRO fleet produced by the compress step.
 """
@@ -65,29 +65,63 @@ def frame_table(n_series):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, a few hundred Hz; falls back
+    to polling nvidia-smi when the NVML binding is unavailable)."""
 
     def __init__(self, gpu):
         self.gpu = gpu
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.stop = False
         self.th = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+        except Exception:
+            self.nvml = None
 
-    def _run(self):
+    def _run_nvml(self):
+        n = self.nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
+        while not self.stop:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.h))
+                for nm, b in bits.items():
+                    if r & b:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _run_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                r = [x.strip() for x in out.split(",")]
+                self.sm.append(float(r[0]))
+                self.mx.append(float(r[1]))
+                for nm, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def __enter__(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th = threading.Thread(target=self._run_nvml if self.nvml else self._run_smi, daemon=True)
         self.th.start()
         return self
 
@@ -96,23 +130,16 @@ class ClockSampler:
         self.th.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for nm, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def cpu_baseline(threads, budget_s=20.0):
     """Oracle port timed on the host cores on a bounded sample of the same workload."""
     import oracle_lib as O
     O.lib()
-    per_class = max(1, threads // 3)
+    per_class = 4 * max(1, threads // 3)
     n = per_class * 3
     arr = np.empty((n, SERIES_LEN))
     make_fleet(n, 5000, arr)
@@ -140,7 +167,7 @@ def run_reference(args):
     import oracle_lib as O
     O.lib()
     threads = os.cpu_count() or 1
-    per_class = max(1, threads // 3)
+    per_class = 4 * max(1, threads // 3)
     n = per_class * 3
     arr = np.empty((n, SERIES_LEN))
     make_fleet(n, 5000, arr)
@@ -171,17 +198,17 @@ def workload_config(series_per_gpu, n_gpus):
                     "frames [131072x7,65536,16384,512,64] per series; subsample of BASELINE config 4 (100k x 1M)",
         "series_per_gpu": series_per_gpu, "series_len": SERIES_LEN, "error_pct": ERROR_PCT, "speed": SPEED,
         "parallelism": f"frames sharded by series over {n_gpus} GPU(s), no collective",
-        "l2_policy": "inputs (>= 768 MB per GPU) exceed the 126 MB L2",
+        "l2_policy": f"inputs ({series_per_gpu * SERIES_LEN * 8 / 1e6:.0f} MB per GPU per step) exceed the 126 MB L2",
     }
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--series", type=int, default=96, help="series per GPU (multiple of 3)")
+    ap.add_argument("--series", type=int, default=288, help="series per GPU (multiple of 3)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -280,13 +307,43 @@ def main():
     dom_ms = kms[dom] / args.steps
     dom_samples = n_samples if dom in ("stats", "select") else fft_samples
     achieved = dom_samples * 8 / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    # the same kernels timed without other waves sharing the GPU (one engine): explains how much of
+    # the in-pipeline duration above is contention
+    iso = None
+    try:
+        os.environ["ATSC_ENGINES"] = "1"
+        ctx1 = atsc_b200.Context([local])
+        for _ in range(2):
+            ctx1.compress_frames(None, offs, lens, atsc_b200.AUTO, ERROR_PCT / 100.0, SPEED, True,
+                                 samples_ptr=dev.data_ptr(), payload_out=pbuf)
+        ctx1.kernel_ms(reset=True)
+        for _ in range(3):
+            ctx1.compress_frames(None, offs, lens, atsc_b200.AUTO, ERROR_PCT / 100.0, SPEED, True,
+                                 samples_ptr=dev.data_ptr(), payload_out=pbuf)
+        k1 = ctx1.kernel_ms(reset=True)
+        ctx1.close()
+        iso = {k: v / 3 for k, v in k1.items() if v}
+    except Exception as ex:  # the figure is explanatory only
+        iso = {"error": str(ex)}
+    finally:
+        os.environ.pop("ATSC_ENGINES", None)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get("k_" + dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_step": dom_samples * 8,
                 "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items() if v},
+                "kernel_ms_per_step_one_engine": iso,
                 "whole_step_frac": n_samples * 8 / (dt / args.steps) / 1e9 / peak,
-                "note": "k_fft is FP32/shared-memory bound (<=24 length-139968 transforms per noisy frame); "
-                        "the HBM line is the task's stated denominator"}
+                "note": "kernel_ms_per_step: CUDA events on each engine's stream inside the timed region (waves of "
+                        "several engines overlap, so the durations include contention and add up to more than the "
+                        "step); k_poly is FP64-latency bound, k_fft_fwd FP32/shared-memory bound, k_stats issue "
+                        "bound (DESIGN.md section 4); the HBM line is the task's stated denominator"}
 
     # ---- decompression of the fleet just produced (device-resident output)
     frames_in, po = [], 0
