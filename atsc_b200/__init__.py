@@ -29,7 +29,7 @@ API_SYMBOLS = [
     "atsc_gpu_compress_series", "atsc_gpu_decompress_series", "atsc_gpu_launch_count", "atsc_gpu_kernel_ms",
     "atsc_plan_shards", "atsc_wbro_decode", "atsc_wbro_encode", "atsc_csv_read_values",
 ]
-KERNEL_NAMES = ["stats", "poly", "rle", "fft", "select", "emit", "decode", "reserved"]
+KERNEL_NAMES = ["stats", "poly", "rle", "fft", "select", "emit", "decode", "host_issue"]
 
 
 class AtscError(RuntimeError):

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -104,7 +105,8 @@ struct Device {
     size_t geoms_uploaded = 0;
     uint64_t launches = 0;
     // CUDA-event time of every kernel (ms accumulated since reset):
-    // 0 stats, 1 plan+poly, 2 rle, 3 fft_fwd+fft, 4 noop+select+scan, 5 emit, 6 decode, 7 unused
+    // 0 stats, 1 plan+poly, 2 rle, 3 fft_small+fft_fwd+fft, 4 noop+select+scan, 5 emit, 6 decode,
+    // 7 HOST time spent preparing and launching waves (not a kernel: shows when a call is host bound)
     double ms[8] = {};
     std::string err;
 };
@@ -420,8 +422,16 @@ bool is_device_ptr(const void *p) {
 // ---------------------------------------------------------------- compress
 // Issues the whole pipeline of one wave on E's stream without waiting for it.  The frames'
 // samples live at d_samples (device).  collect_wave() picks the results up.
+struct HostTimer {
+    double &acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit HostTimer(double &a) : acc(a) {}
+    ~HostTimer() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<FrameReq> &reqs,
                float max_error_f32) {
+    HostTimer host_timer(D.ms[7]);
     const uint32_t n = (uint32_t)reqs.size();
     const double max_err = (double)max_error_f32;  // `max_error as f64` (frame/mod.rs:67,87)
     int rc;

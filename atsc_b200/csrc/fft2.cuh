@@ -333,98 +333,84 @@ template <int RA, int RB>
 __device__ inline void f2_probe_pass1(const double *__restrict__ d, int N, int prefix, const float2 *__restrict__ tw1,
                                       const float2 *__restrict__ T4, float2 *Wp, float2 *sm) {
     static_assert(RA >= 4, "probe needs two distinct output families");
-    constexpr int M1 = RA * RB, P1 = 2 * RB + 1;  // only y[q + RA*t] for the two q is kept: [lc][2][RB]
+    static_assert(F2_M2 * (2 * RB + 1) <= F2_SMEM_F2, "all columns' stage-1 outputs must fit the tile buffer");
+    constexpr int M1 = RA * RB, P1 = 2 * RB + 1;  // only y[q + RA*t] for the two q is kept: [column][2][RB]
     const int tid = threadIdx.x, nth = blockDim.x;
     const bool vec = (((uintptr_t)d >> 3) & 1u) == ((uint32_t)prefix & 1u);
-    for (int c0 = 0; c0 < F2_M2; c0 += F2_TC) {
-        const int nb = min(F2_TC, F2_M2 - c0);
-        for (int item = tid; item < RB * F2_TC; item += nth) {
-            const int lc = item & (F2_TC - 1), p = item / F2_TC;
-            if (lc >= nb) continue;
-            float2 a[RA];
+    // stage 1 for ALL columns (no tile barriers: every thread streams through its items, so the
+    // sample loads of one item overlap the butterflies of the previous one across warps)
+    for (int item = tid; item < RB * F2_M2; item += nth) {
+        const int p = item / F2_M2, c = item - p * F2_M2;
+        float2 a[RA];
 #pragma unroll
-            for (int t = 0; t < RA; t++) a[t] = f2_load_z(d, N, prefix, (p + RB * t) * F2_M2 + c0 + lc, vec);
-            DftS<RA, 1, false>::run(a);  // only outputs 1 and RA-1 are used: the rest is dead code
-            float2 *y = sm + lc * P1;
-            y[p] = cmul(a[1], __ldg(tw1 + p));
-            y[RB + p] = cmul(a[RA - 1], __ldg(tw1 + p * (RA - 1)));
-        }
-        __syncthreads();
-        if (c0 + F2_TC < F2_M2) {
-            for (int i = tid; i < M1 * 4; i += nth) {
-                const int e = i >> 2, ln = i & 3;
-                int ix = 2 * (e * F2_M2 + c0 + F2_TC) - prefix + 16 * ln;
-                ix = min(max(ix, 0), N - 1);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(d + ix));
-            }
-        }
-        for (int item = tid; item < 2 * F2_TC; item += nth) {
-            const int fam = item & 1, lc = item >> 1;  // fam 0: q = 1, fam 1: q = RA-1
-            if (lc >= nb) continue;
-            float2 b[RB];
-            const float2 *y = sm + lc * P1 + fam * RB;
-#pragma unroll
-            for (int t = 0; t < RB; t++) b[t] = y[t];
-            DftS<RB, 1, false>::run(b);
-            const int c = c0 + lc, q = fam ? RA - 1 : 1;
-#pragma unroll
-            for (int u = 0; u < RB; u++) {
-                const int k1 = q + RA * u, lr = fam ? RB + (RB - 1 - u) : u;
-                __stcg(Wp + c * (2 * RB) + lr, cmul(b[u], __ldg(T4 + c * M1 + k1)));
-            }
-        }
-        __syncthreads();
+        for (int t = 0; t < RA; t++) a[t] = f2_load_z(d, N, prefix, (p + RB * t) * F2_M2 + c, vec);
+        DftS<RA, 1, false>::run(a);  // only outputs 1 and RA-1 are used: the rest is dead code
+        float2 *y = sm + c * P1;
+        y[p] = cmul(a[1], __ldg(tw1 + p));
+        y[RB + p] = cmul(a[RA - 1], __ldg(tw1 + p * (RA - 1)));
     }
+    __syncthreads();
+    for (int item = tid; item < 2 * F2_M2; item += nth) {
+        const int fam = item & 1, c = item >> 1;  // fam 0: q = 1, fam 1: q = RA-1
+        float2 b[RB];
+        const float2 *y = sm + c * P1 + fam * RB;
+#pragma unroll
+        for (int t = 0; t < RB; t++) b[t] = y[t];
+        DftS<RB, 1, false>::run(b);
+        const int q = fam ? RA - 1 : 1;
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            const int k1 = q + RA * u, lr = fam ? RB + (RB - 1 - u) : u;
+            __stcg(Wp + c * (2 * RB) + lr, cmul(b[u], __ldg(T4 + c * M1 + k1)));
+        }
+    }
+    __syncthreads();
 }
 
 // count of nonzero bins among the probed rows (this thread's share)
 __device__ inline uint32_t f2_probe_pass2(int M1, int RA, const float2 *__restrict__ tw2, const float2 *__restrict__ twL1,
                                           const float2 *__restrict__ twL2, const float2 *Wp, float2 *sm) {
     const int tid = threadIdx.x, nth = blockDim.x;
-    const int RB = M1 / RA, npairs = RB, stride = 2 * RB;
+    const int RB = M1 / RA, rows = 2 * RB;  // <= 36 rows: one tile (36 * 243 float2 fits the buffer)
     uint32_t nz = 0;
-    for (int pr0 = 0; pr0 < npairs; pr0 += F2_PAIRS) {
-        const int np = min(F2_PAIRS, npairs - pr0);
-        for (int item = tid; item < 9 * 2 * F2_PAIRS; item += nth) {
-            const int lr = item & (2 * F2_PAIRS - 1), p = item / (2 * F2_PAIRS), l = lr & (F2_PAIRS - 1);
-            if (l >= np) continue;
-            const int wl = lr < F2_PAIRS ? pr0 + l : RB + pr0 + l;  // compact row index in Wp
-            float2 a[27];
+    // stage 1: item (p < 9, compact row lr): lr < RB -> k1 = 1 + RA*lr, lr >= RB -> its partner
+    for (int item = tid; item < 9 * rows; item += nth) {
+        const int p = item / rows, lr = item - p * rows;
+        float2 a[27];
 #pragma unroll
-            for (int t = 0; t < 27; t++) a[t] = __ldcg(Wp + (p + 9 * t) * stride + wl);
-            DftS<27, 1, false>::run(a);
-            float2 *y = sm + lr * F2_M2 + 27 * p;
-            y[0] = a[0];
+        for (int t = 0; t < 27; t++) a[t] = __ldcg(Wp + (p + 9 * t) * rows + lr);
+        DftS<27, 1, false>::run(a);
+        float2 *y = sm + lr * F2_M2 + 27 * p;
+        y[0] = a[0];
 #pragma unroll
-            for (int q = 1; q < 27; q++) y[q] = cmul(a[q], __ldg(tw2 + p * q));
-        }
-        __syncthreads();
-        for (int item = tid; item < F2_PAIRS * 27; item += nth) {
-            const int q = item % 27, pl = item / 27;
-            if (pl >= np) continue;
-            float2 A[9], B[9];
-            const float2 *ya = sm + pl * F2_M2 + q, *yb = sm + (pl + F2_PAIRS) * F2_M2 + (26 - q);
-#pragma unroll
-            for (int t = 0; t < 9; t++) {
-                A[t] = ya[27 * t];
-                B[t] = yb[27 * t];
-            }
-            DftS<9, 1, false>::run(A);
-            DftS<9, 1, false>::run(B);
-            const int k1 = 1 + RA * (pr0 + pl);
-            const float2 w1 = __ldg(twL1 + k1);
-#pragma unroll
-            for (int u = 0; u < 9; u++) {
-                const int k2 = q + 27 * u;
-                const float2 w = cmul(w1, __ldg(twL2 + k2));
-                const float2 Xk = f2_post(A[u], B[8 - u], w);
-                const float2 Xm = f2_post(B[8 - u], A[u], make_float2(-w.x, w.y));
-                nz += (Xk.x != 0.f || Xk.y != 0.f) ? 1u : 0u;
-                nz += (Xm.x != 0.f || Xm.y != 0.f) ? 1u : 0u;
-            }
-        }
-        __syncthreads();
+        for (int q = 1; q < 27; q++) y[q] = cmul(a[q], __ldg(tw2 + p * q));
     }
+    __syncthreads();
+    // stage 2: item (pair pl < RB, q < 27): rows k1 (element q) and M1-k1 (element 26-q) together
+    for (int item = tid; item < RB * 27; item += nth) {
+        const int q = item % 27, pl = item / 27;
+        float2 A[9], B[9];
+        const float2 *ya = sm + pl * F2_M2 + q, *yb = sm + (pl + RB) * F2_M2 + (26 - q);
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            A[t] = ya[27 * t];
+            B[t] = yb[27 * t];
+        }
+        DftS<9, 1, false>::run(A);
+        DftS<9, 1, false>::run(B);
+        const int k1 = 1 + RA * pl;
+        const float2 w1 = __ldg(twL1 + k1);
+#pragma unroll
+        for (int u = 0; u < 9; u++) {
+            const int k2 = q + 27 * u;
+            const float2 w = cmul(w1, __ldg(twL2 + k2));
+            const float2 Xk = f2_post(A[u], B[8 - u], w);
+            const float2 Xm = f2_post(B[8 - u], A[u], make_float2(-w.x, w.y));
+            nz += (Xk.x != 0.f || Xk.y != 0.f) ? 1u : 0u;
+            nz += (Xm.x != 0.f || Xm.y != 0.f) ? 1u : 0u;
+        }
+    }
+    __syncthreads();
     return nz;
 }
 

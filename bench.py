@@ -303,7 +303,7 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    dom = max(("stats", "poly", "rle", "fft", "select", "emit"), key=lambda k: kms[k])
+    dom = max(("stats", "poly", "rle", "fft", "select", "emit"), key=lambda k: kms[k])  # host_issue is not a kernel
     dom_ms = kms[dom] / args.steps
     dom_samples = n_samples if dom in ("stats", "select") else fft_samples
     achieved = dom_samples * 8 / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0

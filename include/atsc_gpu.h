@@ -170,7 +170,7 @@ uint64_t atsc_gpu_launch_count(const atsc_ctx *ctx);
 
 /* CUDA-event time (ms, summed over devices, accumulated since the last reset) of each kernel
  * on the library's own streams: [0] stats [1] plan+polynomial [2] rle [3] fft
- * [4] noop-size+select+scan [5] emit [6] decode [7] reserved */
+ * [4] noop-size+select+scan [5] emit [6] decode [7] host time spent preparing and launching waves */
 void atsc_gpu_kernel_ms(atsc_ctx *ctx, double *out8, int reset);
 
 #ifdef __cplusplus
