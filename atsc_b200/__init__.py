@@ -235,16 +235,23 @@ class Context:
         self._check(rc)
         return out, payload[:used.value]
 
-    def decompress_frames(self, frames, payloads, out=None, out_ptr=None, total=None):
-        """atsc_gpu_decompress_frames.  frames: list of (compressor, sample_count, payload_off,
-        payload_len, out_off)."""
-        n = len(frames)
-        arr = (FrameIn * max(n, 1))()
-        need = 0
+    @staticmethod
+    def frames_in(frames):
+        """(compressor, sample_count, payload_off, payload_len, out_off) tuples -> atsc_frame_in array
+        (build it once when the same table is decoded repeatedly)."""
+        arr = (FrameIn * max(len(frames), 1))()
         for i, (c, sc, po, pl, oo) in enumerate(frames):
             arr[i].compressor, arr[i].sample_count, arr[i].payload_off = c, sc, po
             arr[i].payload_len, arr[i].out_off = pl, oo
-            need = max(need, oo + sc)
+        arr.n_frames = len(frames)
+        arr.n_samples = max((oo + sc for _, sc, _, _, oo in frames), default=0)
+        return arr
+
+    def decompress_frames(self, frames, payloads, out=None, out_ptr=None, total=None):
+        """atsc_gpu_decompress_frames.  frames: list of (compressor, sample_count, payload_off,
+        payload_len, out_off), or the array Context.frames_in() made of it."""
+        arr = frames if isinstance(frames, C.Array) else self.frames_in(frames)
+        n, need = arr.n_frames, arr.n_samples
         payloads = np.ascontiguousarray(payloads, dtype=np.uint8)
         if out_ptr is None:
             if out is None:

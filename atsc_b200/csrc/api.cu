@@ -87,6 +87,8 @@ struct Engine {
     // CUDA events around every kernel of the wave (kernel_ms)
     cudaEvent_t ev[10] = {};
     WaveJob job;
+    bool dec_active = false;  // a decode wave is pending on this engine
+    uint32_t dec_pos = 0, dec_n = 0;
 };
 
 struct Device {
@@ -743,18 +745,39 @@ int compress_on_device(Device &D, const double *samples, bool dev_ptr, const uin
 }
 
 // ---------------------------------------------------------------- decompress
+// waits for the decode wave pending on E and checks its per-frame status words
+int collect_decode(Device &D, Engine &E, const uint32_t *idx) {
+    if (!E.dec_active) return ATSC_OK;
+    E.dec_active = false;
+    CK(cudaStreamSynchronize(E.st));
+    CK(cudaGetLastError());
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, E.ev[8], E.ev[9]));
+    D.ms[6] += t;
+    for (uint32_t k = 0; k < E.dec_n; k++)
+        if (E.h_status[k]) {
+            char b[128];
+            snprintf(b, sizeof b, "frame %u: malformed or unsupported payload (code %u)", idx[E.dec_pos + k], E.h_status[k]);
+            D.err = b;
+            return E.h_status[k] == 4 ? ATSC_ERR_UNSUPPORTED : ATSC_ERR_FORMAT;
+        }
+    return ATSC_OK;
+}
+
+// Waves of frames go round the engines like the compress path: payload H2D, k_decode and the
+// output D2H of one wave overlap the other engines' waves.
 int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t *idx, uint32_t m,
                          const uint8_t *payloads, uint64_t payload_bytes, double *out, bool out_dev) {
     CK(cudaSetDevice(D.id));
-    Engine &E = D.eng[0];
-    uint32_t pos = 0;
-    while (pos < m) {
+    uint32_t pos = 0, wave = 0;
+    int rc = ATSC_OK;
+    while (pos < m && !rc) {
         uint64_t tot = 0;
         uint32_t end = pos;
         uint64_t plo = ~0ull, phi = 0;
         while (end < m && end - pos < WAVE_FRAMES) {
             const atsc_frame_in &f = frames[idx[end]];
-            if (tot && tot + f.sample_count > (48ull << 20)) break;
+            if (tot && tot + f.sample_count > D.wave_samples) break;
             tot += f.sample_count;
             plo = std::min<uint64_t>(plo, f.payload_off);
             phi = std::max<uint64_t>(phi, f.payload_off + f.payload_len);
@@ -763,19 +786,22 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
         const uint32_t n = end - pos;
         if (phi > payload_bytes) {
             D.err = "frame payload range exceeds payload_bytes";
-            return ATSC_ERR_ARG;
+            rc = ATSC_ERR_ARG;
+            break;
         }
-        int rc;
+        Engine &E = D.eng[wave % D.n_engines];
+        wave++;
+        if ((rc = collect_decode(D, E, idx))) break;
         size_t hc = E.dec_cap;
-        if ((rc = grow(D, E.st, E.d_dec, E.dec_cap, n))) return rc;
-        if ((rc = grow(D, E.st, E.h_dec, hc, E.dec_cap, true))) return rc;
+        if ((rc = grow(D, E.st, E.d_dec, E.dec_cap, n))) break;
+        if ((rc = grow(D, E.st, E.h_dec, hc, E.dec_cap, true))) break;
         hc = E.status_cap;
-        if ((rc = grow(D, E.st, E.d_status, E.status_cap, n))) return rc;
-        if ((rc = grow(D, E.st, E.h_status, hc, E.status_cap, true))) return rc;
-        if ((rc = grow(D, E.st, E.d_pay_in, E.pay_in_cap, (size_t)(phi - plo) + 64))) return rc;
-        if (!out_dev && (rc = grow(D, E.st, E.d_out, E.out_cap, (size_t)tot + 8))) return rc;
+        if ((rc = grow(D, E.st, E.d_status, E.status_cap, n))) break;
+        if ((rc = grow(D, E.st, E.h_status, hc, E.status_cap, true))) break;
+        if ((rc = grow(D, E.st, E.d_pay_in, E.pay_in_cap, (size_t)(phi - plo) + 64))) break;
+        if (!out_dev && (rc = grow(D, E.st, E.d_out, E.out_cap, (size_t)tot + 8))) break;
         uint64_t oo = 0;
-        for (uint32_t k = 0; k < n; k++) {
+        for (uint32_t k = 0; k < n && !rc; k++) {
             const atsc_frame_in &f = frames[idx[pos + k]];
             DecFrame &d = E.h_dec[k];
             memset(&d, 0, sizeof d);
@@ -788,15 +814,13 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
             d.geom = -1;
             if (f.sample_count == 0 || f.sample_count > (uint32_t)MAX_FRAME) {
                 D.err = "frame sample_count out of range (1..131072)";
-                return ATSC_ERR_ARG;
-            }
-            if (f.compressor == C_FFT && f.sample_count >= 128) {
+                rc = ATSC_ERR_ARG;
+            } else if (f.compressor == C_FFT && f.sample_count >= 128) {
                 int gi;
-                if ((rc = get_geom(D, padded_len(D, f.sample_count), &gi))) return rc;
-                d.geom = gi;
+                if (!(rc = get_geom(D, padded_len(D, f.sample_count), &gi))) d.geom = gi;
             }
         }
-        if ((rc = sync_geoms(D))) return rc;
+        if (rc || (rc = sync_geoms(D))) break;
         CK(cudaMemcpyAsync(E.d_dec, E.h_dec, (size_t)n * sizeof(DecFrame), cudaMemcpyHostToDevice, E.st));
         CK(cudaMemcpyAsync(E.d_pay_in, payloads + plo, (size_t)(phi - plo), cudaMemcpyHostToDevice, E.st));
         CK(cudaMemsetAsync(E.queues, 0, 64 * sizeof(unsigned), E.st));
@@ -823,23 +847,19 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
                 k = j;
             }
         }
-        CK(cudaStreamSynchronize(E.st));
-        CK(cudaGetLastError());
-        {
-            float t = 0.f;
-            CK(cudaEventElapsedTime(&t, E.ev[8], E.ev[9]));
-            D.ms[6] += t;
-        }
-        for (uint32_t k = 0; k < n; k++)
-            if (E.h_status[k]) {
-                char b[128];
-                snprintf(b, sizeof b, "frame %u: malformed or unsupported payload (code %u)", idx[pos + k], E.h_status[k]);
-                D.err = b;
-                return E.h_status[k] == 4 ? ATSC_ERR_UNSUPPORTED : ATSC_ERR_FORMAT;
-            }
+        E.dec_active = true;
+        E.dec_pos = pos;
+        E.dec_n = n;
         pos = end;
     }
-    return ATSC_OK;
+    for (int k = 0; k < D.n_engines; k++) {
+        Engine &E = D.eng[(wave + k) % D.n_engines];
+        int rc2 = rc ? ATSC_OK : collect_decode(D, E, idx);
+        if (rc2) rc = rc2;
+        E.dec_active = false;
+    }
+    for (int k = 0; k < D.n_engines; k++) cudaStreamSynchronize(D.eng[k].st);
+    return rc;
 }
 
 // contiguous ranges of frames balanced by sample count (atsc_plan_shards, ingest.cpp)

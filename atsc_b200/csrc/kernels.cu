@@ -804,7 +804,7 @@ __device__ uint32_t dec_noop(const uint8_t *__restrict__ p, uint32_t len, uint32
 }
 
 __device__ uint32_t dec_poly(const uint8_t *__restrict__ p, uint32_t len, uint32_t N, double *out, double *pts,
-                             const double *__restrict__ inv_d2, DecShared *ds, uint32_t *sh) {
+                             double *tang, const double *__restrict__ inv_d2, DecShared *ds, uint32_t *sh) {
     const uint32_t T = blockDim.x, t = threadIdx.x;
     if (t == 0) {
         uint32_t bad = 0, hdr = 0, K = 0;
@@ -855,11 +855,12 @@ __device__ uint32_t dec_poly(const uint8_t *__restrict__ p, uint32_t len, uint32
     if (step == 0) return 5;  // step_by(0) panics in the reference
     PolyKeys k = poly_keys(N, step);
     if (K != k.K) return 5;
-    auto pf = [&](uint32_t j) { return pts[j]; };
-    for (uint32_t x = t; x < N; x += T) {
-        double v = ptype ? idw_eval_at(k, x, pf, inv_d2) : poly_eval_at(k, x, pf);
-        out[x] = round_and_limit5(v, vmin, vmax);
+    if (!ptype) {
+        poly_expand(pts, k, vmin, vmax, tang, out);
+        return 0;
     }
+    auto pf = [&](uint32_t j) { return pts[j]; };
+    for (uint32_t x = t; x < N; x += T) out[x] = round_and_limit5(idw_eval_at(k, x, pf, inv_d2), vmin, vmax);
     return 0;
 }
 
@@ -1047,6 +1048,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_decode(const DecFrame *__res
     uint32_t *sh = (uint32_t *)shd;
     FftWs fws = fft_slot(pool, blockIdx.x);
     double *pts = pool.dec_pts + (size_t)blockIdx.x * (MAX_FRAME + 8);
+    double *tang = pool.poly_slope + (size_t)blockIdx.x * (MAX_FRAME + 8);
     uint32_t *mark = pool.dec_mark + (size_t)blockIdx.x * (MAX_FRAME + 8);
     uint32_t *idxs = pool.dec_idx + (size_t)blockIdx.x * (MAX_FRAME + 8);
     for (;;) {
@@ -1060,7 +1062,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_decode(const DecFrame *__res
             case C_CONSTANT: rc = dec_constant(p, f.payload_len, f.sample_count, o, &ds); break;
             case C_NOOP: rc = dec_noop(p, f.payload_len, f.sample_count, o, &ds, sh); break;
             case C_POLY:
-            case C_IDW: rc = dec_poly(p, f.payload_len, f.sample_count, o, pts, inv_d2, &ds, sh); break;
+            case C_IDW: rc = dec_poly(p, f.payload_len, f.sample_count, o, pts, tang, inv_d2, &ds, sh); break;
             case C_RLE: rc = dec_rle(p, f.payload_len, f.sample_count, o, pts, idxs, mark, &ds, sh); break;
             case C_FFT: rc = dec_fft(p, f.payload_len, f.sample_count, o, geoms, f.geom, fws, dyn_f2, &ds, sh, &sg); break;
             default: rc = 4; break;

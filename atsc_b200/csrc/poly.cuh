@@ -191,6 +191,56 @@ __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys 
     return __ddiv_rn(s, (double)N);
 }
 
+// Polynomial::polynomial_to_data (polynomial.rs:342-373) + round_and_limit_f64 for a whole frame:
+// out[x] for x < N from the K decoded key values pts[] -- the decompressor's hot loop.  Same value
+// arithmetic as poly_eval_at (same operations, same order; the final quotient by 1e5 is the
+// correctly rounded one, div_1e5), organised like poly_mape: thread t owns one offset inside the
+// segments, tangents come from a pre-pass.  All threads call.
+__device__ inline void poly_expand(const double *__restrict__ pts, const PolyKeys &k, double vmin, double vmax,
+                                   double *__restrict__ tang, double *__restrict__ out) {
+    const uint32_t N = k.N, step = k.step, K = k.K, T = blockDim.x, t = threadIdx.x;
+    auto pf = [&](uint32_t j) { return pts[j]; };
+    auto fin = [&](double v) {
+        double o = div_1e5(round_half_away(__dmul_rn(v, 100000.0)));
+        if (o < vmin) return vmin;
+        if (o > vmax) return vmax;
+        return o;
+    };
+    if (step >= (uint32_t)POLY_MAXSTEP || K < 4) {
+        for (uint32_t x = t; x < N; x += T) out[x] = fin(poly_eval_at(k, x, pf));
+        return;
+    }
+    const double stepd = (double)step;
+    for (uint32_t j = 1 + t; j + 1 < K; j += T) {
+        uint32_t pa = poly_pos(k, j - 1), pb = poly_pos(k, j + 1);
+        tang[j] = __dmul_rn(__ddiv_rn(__dsub_rn(pts[j + 1], pts[j - 1]), __dsub_rn((double)pb, (double)pa)), stepd);
+    }
+    __syncthreads();
+    const uint32_t G = T / step, g = t / step, j = t - g * step;
+    if (g < G) {
+        const double tt = __ddiv_rn((double)j, stepd);
+        const double two_t = __dmul_rn(tt, 2.0), three_t = __dmul_rn(tt, 3.0);
+        const double t2 = __dmul_rn(tt, tt), t3 = __dmul_rn(t2, tt);
+        const double two_t3 = __dmul_rn(t2, two_t), two_t2 = __dmul_rn(tt, two_t), three_t2 = __dmul_rn(tt, three_t);
+        const double h00 = __dadd_rn(__dsub_rn(two_t3, three_t2), 1.0), h10 = __dadd_rn(__dsub_rn(t3, two_t2), tt);
+        const double h01 = __dsub_rn(three_t2, two_t3), h11 = __dsub_rn(t3, t2);
+        // Catmull-Rom segments 1 .. K-3 (polynomial.rs:349): keys i and i+1 are regular
+#pragma unroll 2
+        for (uint32_t i = 1 + g; i + 3 <= K; i += G) {
+            const double av = pts[i], bv = pts[i + 1];
+            const double v = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(av, h00), __dmul_rn(tang[i], h10)), __dmul_rn(bv, h01)),
+                                       __dmul_rn(tang[i + 1], h11));
+            out[i * step + j] = fin(v);
+        }
+    }
+    // the Linear ends: segment 0, segment K-2 (possibly irregular), the last sample
+    const uint32_t start_last = (K - 2) * step, nA = step, nB = N - start_last;
+    for (uint32_t e = t; e < nA + nB; e += T) {
+        const uint32_t x = e < nA ? e : start_last + (e - nA);
+        out[x] = fin(poly_eval_at(k, x, pf));
+    }
+}
+
 // payload size of a Polynomial struct (polynomial.rs:54-87) with K points at `step`
 __device__ inline uint32_t poly_payload_size(const double *__restrict__ d, const PolyKeys &k,
                                              int bitdepth, bool no_points, uint32_t *scratch) {
