@@ -282,11 +282,16 @@ int get_geom(Device &D, uint32_t L, int *out_idx) {
     if ((rc = upload_vec(D, twA, &g.twA))) return rc;
     if ((rc = upload_vec(D, twB, &g.twB))) return rc;
     g.T4 = nullptr;
+    g.T4T = nullptr;
     if (fast) {
         std::vector<float2> T4((size_t)g.M);
         for (uint32_t n2 = 0; n2 < g.M2; n2++)
             for (uint32_t k1 = 0; k1 < g.M1; k1++) T4[(size_t)n2 * g.M1 + k1] = root((double)(((uint64_t)k1 * n2) % g.M), g.M);
         if ((rc = upload_vec(D, T4, &g.T4))) return rc;
+        std::vector<float2> T4T((size_t)g.M);
+        for (uint32_t k1 = 0; k1 < g.M1; k1++)
+            for (uint32_t n2 = 0; n2 < g.M2; n2++) T4T[(size_t)k1 * g.M2 + n2] = T4[(size_t)n2 * g.M1 + k1];
+        if ((rc = upload_vec(D, T4T, &g.T4T))) return rc;
     }
     int idx = (int)D.geoms_host.size();
     D.geoms_host.push_back(g);

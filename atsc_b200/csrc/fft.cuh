@@ -54,6 +54,7 @@ struct FftGeom {
     const float2 *twA;  // [M1][32]: exp(-2 pi i e f / M)
     const float2 *twB;  // [M2][32]
     const float2 *T4;   // [M2][M1] four-step twiddle exp(-2 pi i k1 n2 / M), column-major (fft2.cuh); nullptr = none
+    const float2 *T4T;  // [M1][M2] the same table, row-major (inverse, fft2.cuh)
 };
 
 // per-CTA-slot global workspace

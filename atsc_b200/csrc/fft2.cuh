@@ -414,6 +414,138 @@ __device__ inline uint32_t f2_probe_pass2(int M1, int RA, const float2 *__restri
     return nz;
 }
 
+// ---------------------------------------------------------------------------------------
+// INVERSE of the first `c` list entries (the refinement loop's per-iteration transform):
+// Epi(j, value) is called once for every time index j < L with the unnormalised real output.
+// Mirror image of the forward engine with conjugated roots:
+//   pass 1'  rows k1:    sparse list -> zero-filled smem tile (scatter coefficients of
+//            fft_prepare_entries) -> registers (radix 27) -> smem -> registers (radix 9) -> W[k1][n2]
+//   pass 2'  columns n2: W * conj(T4T) -> registers (radix RA) -> smem -> registers (radix RB)
+//            -> epilogue on samples 2n, 2n+1 (n = n1*243 + n2), 32 consecutive columns per warp.
+// Written for any block size (item loops); tile sizes assume <= 512 threads hold one pass-1' item each.
+// ---------------------------------------------------------------------------------------
+constexpr int F2I_TR = 56;   // rows per pass-1' tile: 9 * 56 = 504 radix-27 items
+constexpr int F2I_TC = 28;   // columns per pass-2' tile: 18 * 28 = 504 radix-16 items
+constexpr int F2I_SMEM_F2 = F2I_TR * F2_M2;  // 13,608 float2 = 108,864 B  (>= 28 * 289)
+
+template <int RA, int RB, class Epi>
+__device__ inline void f2_inv_pass2(const float2 *__restrict__ tw1, const float2 *__restrict__ T4T, const float2 *W,
+                                    float2 *sm, Epi epi) {
+    constexpr int M1 = RA * RB, P1 = M1 + 1;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int c0 = 0; c0 < F2_M2; c0 += F2I_TC) {
+        const int nb = min(F2I_TC, F2_M2 - c0);
+        // stage 1: item (p < RB, column lc), lc fastest: radix RA over rows k1 = p + RB*t
+        for (int item = tid; item < RB * nb; item += nth) {
+            const int p = item / nb, lc = item - p * nb;
+            float2 a[RA];
+#pragma unroll
+            for (int t = 0; t < RA; t++) {
+                const int i = (p + RB * t) * F2_M2 + c0 + lc;
+                a[t] = cmulc(__ldcg(W + i), __ldg(T4T + i));  // four-step twiddle exp(+2 pi i k1 n2 / M)
+            }
+            DftS<RA, 1, true>::run(a);
+            float2 *y = sm + lc * P1 + RA * p;
+            y[0] = a[0];
+#pragma unroll
+            for (int q = 1; q < RA; q++) y[q] = cmulc(a[q], __ldg(tw1 + p * q));
+        }
+        __syncthreads();
+        // stage 2: item (q < RA, column lc), lc fastest: radix RB over y[q + RA*t] -> n1 = q + RA*u
+        for (int item = tid; item < RA * nb; item += nth) {
+            const int q = item / nb, lc = item - q * nb;
+            float2 b[RB];
+            const float2 *y = sm + lc * P1 + q;
+#pragma unroll
+            for (int t = 0; t < RB; t++) b[t] = y[RA * t];
+            DftS<RB, 1, true>::run(b);
+#pragma unroll
+            for (int u = 0; u < RB; u++) {
+                const uint32_t n = (uint32_t)((q + RA * u) * F2_M2 + c0 + lc);
+                epi(2 * n, b[u].x);
+                epi(2 * n + 1, b[u].y);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <class Epi>
+__device__ inline void f2_inverse(const FftGeom &g, FftWs ws, uint32_t c, float2 *sm, Epi epi) {
+    const int M1 = (int)g.M1;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const float2 *__restrict__ tw2 = g.tw2;
+    // ---- pass 1': row tiles built from the sparse list
+    for (int r0 = 0; r0 < M1; r0 += F2I_TR) {
+        const int nb = min(F2I_TR, M1 - r0);
+        for (int i = tid; i < nb * F2_M2; i += nth) sm[i] = make_float2(0.f, 0.f);
+        __syncthreads();
+        for (uint32_t r = tid; r < c; r += nth) {
+            const uint32_t ov = ws.ovr[r];
+            if (ov > r && ov < c) continue;  // overwritten by a later aliased entry (fft.rs:411-420)
+            const uint32_t l = ws.locD[r];
+            if (l != 0xFFFFFFFFu) {
+                const uint32_t f = (l >> 16) - (uint32_t)r0;
+                if (f < (uint32_t)nb) sm[f * F2_M2 + (l & 0xFFFFu)] = ws.cD[r];
+            }
+        }
+        __syncthreads();
+        for (uint32_t r = tid; r < c; r += nth) {
+            const uint32_t ov = ws.ovr[r];
+            if (ov > r && ov < c) continue;
+            const uint32_t l = ws.locM[r];
+            if (l != 0xFFFFFFFFu) {
+                const uint32_t f = (l >> 16) - (uint32_t)r0;
+                if (f < (uint32_t)nb) {
+                    float2 *q = &sm[f * F2_M2 + (l & 0xFFFFu)];
+                    *q = cadd(*q, ws.cM[r]);
+                }
+            }
+        }
+        __syncthreads();
+        // stage 1 (in place: every item is read into registers before any is written back)
+        for (int base = 0; base < 9 * nb; base += nth) {
+            const int item = base + tid;
+            const bool on = item < 9 * nb;
+            const int p = on ? item / nb : 0, lr = on ? item - p * nb : 0;
+            float2 a[27];
+            if (on) {
+#pragma unroll
+                for (int t = 0; t < 27; t++) a[t] = sm[lr * F2_M2 + p + 9 * t];
+                DftS<27, 1, true>::run(a);
+            }
+            __syncthreads();
+            if (on) {
+                float2 *y = sm + lr * F2_M2 + 27 * p;
+                y[0] = a[0];
+#pragma unroll
+                for (int q = 1; q < 27; q++) y[q] = cmulc(a[q], __ldg(tw2 + p * q));
+            }
+            __syncthreads();
+        }
+        // stage 2: item (row lr, q < 27), q fastest: radix 9 over y[q + 27 t] -> n2 = q + 27 u
+        for (int item = tid; item < nb * 27; item += nth) {
+            const int lr = item / 27, q = item - lr * 27;
+            float2 b[9];
+#pragma unroll
+            for (int t = 0; t < 9; t++) b[t] = sm[lr * F2_M2 + q + 27 * t];
+            DftS<9, 1, true>::run(b);
+            float2 *o = ws.W + (size_t)(r0 + lr) * F2_M2 + q;
+#pragma unroll
+            for (int u = 0; u < 9; u++) __stcg(o + 27 * u, b[u]);
+        }
+        __syncthreads();
+    }
+    // ---- pass 2': column tiles + epilogue
+    switch (M1) {
+        case 288: f2_inv_pass2<16, 18>(g.tw1, g.T4T, ws.W, sm, epi); break;
+        case 144: f2_inv_pass2<16, 9>(g.tw1, g.T4T, ws.W, sm, epi); break;
+        case 72: f2_inv_pass2<8, 9>(g.tw1, g.T4T, ws.W, sm, epi); break;
+        case 36: f2_inv_pass2<4, 9>(g.tw1, g.T4T, ws.W, sm, epi); break;
+        default: f2_inv_pass2<2, 9>(g.tw1, g.T4T, ws.W, sm, epi); break;
+    }
+}
+
 __device__ inline bool f2_supported(const FftGeom &g) {
     return g.real && g.M2 == (uint32_t)F2_M2 && g.T4 != nullptr &&
            (g.M1 == 288u || g.M1 == 144u || g.M1 == 72u || g.M1 == 36u || g.M1 == 18u);

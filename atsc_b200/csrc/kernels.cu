@@ -148,6 +148,8 @@ __global__ void __launch_bounds__(BLOCK) k_rle(FrameWork *fr, uint32_t n, const 
 // =========================================================================================
 // fft
 // =========================================================================================
+// k_fft: one 512-thread CTA per SM (128 registers for the radix-27 butterflies of f2_inverse)
+constexpr int K_FFT_SMEM_BYTES = F2I_SMEM_F2 * (int)sizeof(float2) > FFT_SMEM_BYTES ? F2I_SMEM_F2 * (int)sizeof(float2) : FFT_SMEM_BYTES;
 __device__ inline bool fft_loop_near_tie(double cur, int E) {
     if (!(cur == cur) || isinf(cur)) return false;
     double c = cur * 1000.0;
@@ -304,7 +306,10 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
             acc += mape_term(out, o);
         };
         if (gi >= 0) {
-            fft_inverse(*sg, ws, c, sm, epi, d, N, prefix);
+            if (sg->T4T)
+                f2_inverse(*sg, ws, c, sm, epi);  // register-radix inverse (fft2.cuh)
+            else
+                fft_inverse(*sg, ws, c, sm, epi, d, N, prefix);
         } else {
             for (uint32_t j = t; j < N; j += T) {
                 float v = 0.f;
@@ -364,7 +369,7 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
     }
 }
 
-__global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
+__global__ void __launch_bounds__(FFT_THREADS, 1) k_fft(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
                                                double max_err, const FftGeom *__restrict__ geoms, SlotPool pool,
                                                FftEntry *arena, float2 *spec_xd, uint32_t *spec_keys, unsigned *q) {
     extern __shared__ float2 dyn_f2[];
@@ -1095,7 +1100,7 @@ static int sms() {
 
 int kernels_init() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_SMEM_BYTES);
+    e = cudaFuncSetAttribute(k_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, K_FFT_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
@@ -1128,7 +1133,7 @@ void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err
 }
 void launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
                 SlotPool pool, FftEntry *arena, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st) {
-    k_fft<<<grid_for(n, pool.fft_slots), FFT_THREADS, FFT_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool, arena,
+    k_fft<<<grid_for(n, pool.fft_slots / 2), FFT_THREADS, K_FFT_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool, arena,
                                                                            spec_xd, spec_keys, q);
 }
 void launch_fft_small(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
