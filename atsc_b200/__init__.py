@@ -27,7 +27,7 @@ API_SYMBOLS = [
     "atsc_gpu_create", "atsc_gpu_destroy", "atsc_gpu_last_error", "atsc_gpu_host_alloc", "atsc_gpu_host_free",
     "atsc_gpu_compress_frames", "atsc_gpu_decompress_frames", "atsc_plan_chunk_sizes",
     "atsc_gpu_compress_series", "atsc_gpu_decompress_series", "atsc_gpu_launch_count", "atsc_gpu_kernel_ms",
-    "atsc_plan_shards", "atsc_wbro_decode", "atsc_wbro_encode", "atsc_csv_read_values",
+    "atsc_plan_shards", "atsc_wbro_decode", "atsc_wbro_encode", "atsc_csv_read_values", "atsc_gpu_last_call_ms",
 ]
 KERNEL_NAMES = ["stats", "poly", "rle", "fft", "select", "emit", "decode", "host_issue"]
 
@@ -88,6 +88,8 @@ def load_library(build_if_missing=True):
     L.atsc_wbro_encode.argtypes = [vp, C.c_uint64, vp, C.c_uint64]
     L.atsc_csv_read_values.restype = C.c_int64
     L.atsc_csv_read_values.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_char_p, C.c_char_p, vp, C.c_uint64]
+    L.atsc_gpu_last_call_ms.restype = C.c_double
+    L.atsc_gpu_last_call_ms.argtypes = [vp]
     L.atsc_gpu_kernel_ms.restype = None
     L.atsc_gpu_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
     L.atsc_gpu_compress_frames.restype = C.c_int
@@ -200,6 +202,11 @@ class Context:
     @property
     def launches(self):
         return int(self.L.atsc_gpu_launch_count(self.h))
+
+    @property
+    def last_call_ms(self):
+        """Device span (CUDA events) of the last compress / decompress call, ms."""
+        return float(self.L.atsc_gpu_last_call_ms(self.h))
 
     def kernel_ms(self, reset=True):
         """CUDA-event milliseconds per kernel since the last reset (dict by kernel name)."""

@@ -106,6 +106,9 @@ struct Device {
     FftGeom *geoms_dev = nullptr;  // GEOM_CAP entries, appended to (never reallocated: waves in flight read it)
     size_t geoms_uploaded = 0;
     uint64_t launches = 0;
+    // device span of the last compress / decompress call: first operation issued -> last one done
+    cudaEvent_t ev_begin = nullptr, ev_end[MAX_ENGINES] = {};
+    double last_call_ms = 0.0;
     // CUDA-event time of every kernel (ms accumulated since reset):
     // 0 stats, 1 plan+poly, 2 rle, 3 fft_small+fft_fwd+fft, 4 noop+select+scan, 5 emit, 6 decode,
     // 7 HOST time spent preparing and launching waves (not a kernel: shows when a call is host bound)
@@ -384,6 +387,8 @@ int device_init(Device &D) {
     D.wave_samples = (uint64_t)env_int("ATSC_WAVE_MI", 72, 1, 512) << 20;
     for (int e = 0; e < D.n_engines; e++)
         if ((rc = engine_init(D, D.eng[e], sms))) return rc;
+    CK(cudaEventCreate(&D.ev_begin));
+    for (int e = 0; e < D.n_engines; e++) CK(cudaEventCreate(&D.ev_end[e]));
     CK(cudaMalloc((void **)&D.geoms_dev, GEOM_CAP * sizeof(FftGeom)));
     CK(cudaMalloc((void **)&D.inv_d2, (size_t)(MAX_FRAME + 8) * 8));
     launch_inv_d2(D.inv_d2, MAX_FRAME + 8, D.st);
@@ -411,6 +416,9 @@ void device_free(Device &D) {
             if (ev) cudaEventDestroy(ev);
         if (E.st) cudaStreamDestroy(E.st);
     }
+    if (D.ev_begin) cudaEventDestroy(D.ev_begin);
+    for (auto &ev : D.ev_end)
+        if (ev) cudaEventDestroy(ev);
     if (D.inv_d2) cudaFree(D.inv_d2);
     if (D.geoms_dev) cudaFree(D.geoms_dev);
     for (void *p : D.geom_allocs) cudaFree(p);
@@ -424,6 +432,25 @@ bool is_device_ptr(const void *p) {
         return false;
     }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// device span of a call: begin is recorded on the first engine's stream before anything is issued,
+// an end event on every engine's stream after its last operation
+int span_begin(Device &D) {
+    CK(cudaEventRecord(D.ev_begin, D.eng[0].st));
+    return ATSC_OK;
+}
+int span_end(Device &D) {
+    for (int k = 0; k < D.n_engines; k++) CK(cudaEventRecord(D.ev_end[k], D.eng[k].st));
+    double ms = 0.0;
+    for (int k = 0; k < D.n_engines; k++) {
+        CK(cudaStreamSynchronize(D.eng[k].st));
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, D.ev_begin, D.ev_end[k]));
+        ms = std::max(ms, (double)t);
+    }
+    D.last_call_ms = ms;
+    return ATSC_OK;
 }
 
 // ---------------------------------------------------------------- compress
@@ -516,8 +543,6 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     launch_plan(E.d_frames, n, d_samples, E.d_parts, st);
     launch_poly(E.d_frames, n, d_samples, max_err, D.inv_d2, E.pool, E.queues + 1, st);
     CK(cudaEventRecord(E.ev[2], st));
-    launch_rle(E.d_frames, n, d_samples, max_err, E.pool, E.queues + 2, st);
-    CK(cudaEventRecord(E.ev[3], st));
     if (any_small) {
         launch_fft_small(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.d_arena, small_lmax, E.queues + 8, st);
         D.launches++;
@@ -530,6 +555,9 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
         launch_fft(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_arena, E.d_spec_xd, E.d_spec_keys, E.queues + 3, st);
         D.launches++;
     }
+    CK(cudaEventRecord(E.ev[3], st));
+    // RLE last: its sort runs only for frames where a size lower bound still beats Polynomial and FFT
+    launch_rle(E.d_frames, n, d_samples, max_err, E.pool, E.queues + 2, st);
     CK(cudaEventRecord(E.ev[4], st));
     D.launches += 4;
     if (any_noop) {
@@ -559,7 +587,7 @@ int wait_wave(Device &D, Engine &E, uint32_t n, const double *d_samples, uint64_
     for (int k = 0; k < 5; k++) {
         float t = 0.f;
         CK(cudaEventElapsedTime(&t, E.ev[k], E.ev[k + 1]));
-        D.ms[k] += t;
+        D.ms[k == 2 ? 3 : k == 3 ? 2 : k] += t;  // the FFT kernels run before k_rle
     }
     float te = 0.f;
     CK(cudaEventElapsedTime(&te, E.ev[6], E.ev[7]));
@@ -644,7 +672,8 @@ int compress_on_device(Device &D, const double *samples, bool dev_ptr, const uin
     uint32_t pos = 0, wave = 0;
     std::vector<FrameReq> sel;
     std::vector<uint32_t> sel_of;
-    int rc = ATSC_OK;
+    int rc = span_begin(D);
+    if (rc) return rc;
     while (pos < m) {
         // ---- cut a wave
         uint64_t tot = 0;
@@ -744,7 +773,8 @@ int compress_on_device(Device &D, const double *samples, bool dev_ptr, const uin
         if (rc2) rc = rc2;
         E.job.active = false;
     }
-    for (int k = 0; k < D.n_engines; k++) cudaStreamSynchronize(D.eng[k].st);
+    int rc3 = span_end(D);
+    if (!rc) rc = rc3;
     if (!rc) CK(cudaGetLastError());
     return rc;
 }
@@ -775,7 +805,7 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
                          const uint8_t *payloads, uint64_t payload_bytes, double *out, bool out_dev) {
     CK(cudaSetDevice(D.id));
     uint32_t pos = 0, wave = 0;
-    int rc = ATSC_OK;
+    int rc = span_begin(D);
     while (pos < m && !rc) {
         uint64_t tot = 0;
         uint32_t end = pos;
@@ -863,7 +893,8 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
         if (rc2) rc = rc2;
         E.dec_active = false;
     }
-    for (int k = 0; k < D.n_engines; k++) cudaStreamSynchronize(D.eng[k].st);
+    int rc3 = span_end(D);
+    if (!rc) rc = rc3;
     return rc;
 }
 
@@ -939,6 +970,13 @@ uint64_t atsc_gpu_launch_count(const atsc_ctx *ctx) {
     if (ctx)
         for (Device *D : ctx->devs) n += D->launches;
     return n;
+}
+
+double atsc_gpu_last_call_ms(const atsc_ctx *ctx) {
+    double ms = 0.0;
+    if (ctx)
+        for (Device *D : ctx->devs) ms = std::max(ms, D->last_call_ms);
+    return ms;
 }
 
 void atsc_gpu_kernel_ms(atsc_ctx *ctx, double *out8, int reset) {

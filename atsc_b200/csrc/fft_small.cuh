@@ -164,7 +164,7 @@ __device__ inline void fft_small_frame(const double *__restrict__ d, FrameWork *
     uint32_t bound = 0xFFFFFFFFu;
     if (bounded && fw->comp == C_AUTO && fw->forced == 0xFF) {
         if (fw->poly_valid == 1 && fw->poly_err <= max_err) bound = min(bound, fw->poly_size);
-        if (fw->rle_valid == 1) bound = min(bound, fw->rle_size);
+        if (fw->need_rle) bound = min(bound, fw->rle_valid == 1 ? fw->rle_size : rle_upper_bound(fw));  // RLE's error is 0: it always passes
     }
     const uint32_t kcap = min(min(kmax, fw->fft_list_cap), (uint32_t)FS_KMAX);
     if (bound != 0xFFFFFFFFu) {

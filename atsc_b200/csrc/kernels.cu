@@ -129,11 +129,16 @@ __global__ void __launch_bounds__(BLOCK) k_rle(FrameWork *fr, uint32_t n, const 
         if (i >= (int)n) break;
         FrameWork *fw = &fr[i];
         if (!fw->need_rle) continue;
-        if (fw->comp == C_AUTO && fw->forced == 0xFF && fw->poly_valid == 1 && fw->poly_err <= max_err) {
-            // Polynomial precedes RLE in the candidate list (frame/mod.rs:77) and min_by_key keeps
-            // the first minimum, so RLE can only win with a strictly smaller payload.
+        if (fw->comp == C_AUTO && fw->forced == 0xFF) {
+            // RLE comes last in the candidate list (frame/mod.rs:77) and min_by_key keeps the first
+            // minimum, so it can only win with a strictly smaller payload than every passing
+            // candidate before it.  Polynomial and FFT have already run: when even a lower bound of
+            // the RLE size loses, the sort is skipped.
+            uint32_t best = 0xFFFFFFFFu;
+            if (fw->poly_valid == 1 && fw->poly_err <= max_err) best = min(best, fw->poly_size);
+            if (fw->fft_valid == 1 && fw->fft_err <= max_err) best = min(best, fw->fft_size);
             uint32_t lb = rle_lower_bound(fw);
-            if (lb >= fw->poly_size) {
+            if (lb >= best) {
                 if (threadIdx.x == 0) {
                     fw->rle_valid = 2;
                     fw->rle_size = lb;
@@ -219,7 +224,7 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
     uint32_t bound = 0xFFFFFFFFu;
     if (bounded && fw->comp == C_AUTO && fw->forced == 0xFF) {
         if (fw->poly_valid == 1 && fw->poly_err <= max_err) bound = min(bound, fw->poly_size);
-        if (fw->rle_valid == 1) bound = min(bound, fw->rle_size);
+        if (fw->need_rle) bound = min(bound, fw->rle_valid == 1 ? fw->rle_size : rle_upper_bound(fw));  // RLE's error is 0: it always passes
     }
     if (bound != 0xFFFFFFFFu && !fw->fwd_done) {
         // Early exit before any sorting: the first schedule point keeps c1 = min(max_freq, #nonzero
@@ -433,7 +438,7 @@ __global__ void __launch_bounds__(F2_THREADS, 2) k_fft_fwd(FrameWork *fr, uint32
         uint32_t bound = 0xFFFFFFFFu;
         if (bounded && fw->comp == C_AUTO && fw->forced == 0xFF) {
             if (fw->poly_valid == 1 && fw->poly_err <= max_err) bound = min(bound, fw->poly_size);
-            if (fw->rle_valid == 1) bound = min(bound, fw->rle_size);
+            if (fw->need_rle) bound = min(bound, fw->rle_valid == 1 ? fw->rle_size : rle_upper_bound(fw));  // RLE's error is 0: it always passes
         }
         if (bound != 0xFFFFFFFFu) {
             // The first schedule point keeps c1 = min(max_freq, #nonzero bins) entries (fft.rs:249-252),

@@ -22,6 +22,15 @@ __device__ inline uint32_t rle_lower_bound(const FrameWork *fw) {
     return 2u + 1u + groups * (minvb + 1u) + fw->rle_idx_bytes;
 }
 
+// upper bound of the RLE payload size without grouping: every run its own group (a merged group
+// of c runs costs one value + varint(c) instead of c values + c count bytes, never more).  The
+// FFT candidate, which runs BEFORE the RLE sort, is pruned against this figure.
+__device__ inline uint32_t rle_upper_bound(const FrameWork *fw) {
+    const uint32_t maxvb = fw->bitdepth == BD_F64 ? 8u : fw->bitdepth == BD_I32 ? 5u : fw->bitdepth == BD_I16 ? 3u : 1u;
+    const unsigned long long ub = 2ull + 5ull + (unsigned long long)fw->n_runs * (maxvb + 1u) + fw->rle_idx_bytes;
+    return ub > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)ub;
+}
+
 // All threads of the CTA call.  Returns the exact payload size; if out != nullptr also
 // writes the payload.  sh: 128-word static scratch; hist: RLE_HIST_WORDS words.
 __device__ inline uint32_t rle_process(const double *__restrict__ d, FrameWork *fw, RleWs ws,

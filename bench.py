@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--series", type=int, default=288, help="series per GPU (multiple of 3)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--as-rank", type=int, default=None, help="diagnostic: generate the fleet rank R of a multi-GPU run would get")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -226,6 +227,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     warmup = max(args.warmup, 3)
     S = args.series
@@ -237,7 +239,7 @@ def main():
     hptr = L.atsc_gpu_host_alloc(nbytes)
     import ctypes as C
     host = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_double)), shape=(S, SERIES_LEN))
-    make_fleet(S, 5000 + rank * S, host)
+    make_fleet(S, 5000 + (rank if args.as_rank is None else args.as_rank) * S, host)
     dev = torch.empty(S * SERIES_LEN, dtype=torch.float64, device="cuda")
     dev.copy_(torch.from_numpy(host.reshape(-1)))
     torch.cuda.synchronize()
@@ -263,17 +265,29 @@ def main():
         return ctx.compress_frames(host.reshape(-1), offs, lens, atsc_b200.AUTO, ERROR_PCT / 100.0, SPEED, True,
                                    payload_out=pbuf)
 
-    def timed(fn, steps):
+    dev_ms = {}
+
+    def timed(fn, steps, tag=None):
+        """K steps bracketed by barrier + synchronize; returns (wall seconds, max over ranks; last result).
+        The library's own CUDA events give the device span of every call (dev_ms[tag] = their sum, max over
+        ranks): the two differ only by the host gaps between calls."""
         barrier()
         t0 = time.perf_counter()
+        span = 0.0
         for _ in range(steps):
             r = fn()
+            span += ctx.last_call_ms
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            t = torch.tensor([dt, span], dtype=torch.float64, device="cuda")
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            if tag:
+                dev_ms[tag + "_per_rank"] = [round(float(x[1].item()) / steps, 4) for x in allt]
+            dt, span = max(float(x[0].item()) for x in allt), max(float(x[1].item()) for x in allt)
+        if tag:
+            dev_ms[tag] = span / steps
         return dt, r
 
     for _ in range(warmup):
@@ -281,7 +295,7 @@ def main():
     ctx.kernel_ms(reset=True)
     l0 = ctx.launches
     with ClockSampler(local) as clk:
-        dt, (out, payload) = timed(step_dev, args.steps)
+        dt, (out, payload) = timed(step_dev, args.steps, "compress")
     launches = ctx.launches - l0
     kms = ctx.kernel_ms(reset=True)
     value = world * n_samples * args.steps / dt / 1e6
@@ -289,7 +303,7 @@ def main():
     # ---- e2e: host buffers, H2D inside
     for _ in range(2):
         step_host()
-    dt_e2e, _ = timed(step_host, args.steps)
+    dt_e2e, _ = timed(step_host, args.steps, "compress_e2e")
     e2e_v = world * n_samples * args.steps / dt_e2e / 1e6
     d2h = int(len(payload)) + len(lens) * 168
 
@@ -357,7 +371,7 @@ def main():
     for _ in range(2):
         ctx.decompress_frames(frames_in, payload, out_ptr=dout.data_ptr())
     ctx.kernel_ms(reset=True)
-    dt_dec, _ = timed(lambda: ctx.decompress_frames(frames_in, payload, out_ptr=dout.data_ptr()), args.steps)
+    dt_dec, _ = timed(lambda: ctx.decompress_frames(frames_in, payload, out_ptr=dout.data_ptr()), args.steps, "decompress")
     dec_ms = ctx.kernel_ms(reset=True)["decode"] / args.steps
     hout = host.reshape(-1)  # page-locked; the input fleet is no longer needed
     dt_dec_e2e, _ = timed(lambda: ctx.decompress_frames(frames_in, payload, out=hout), max(1, args.steps // 2))
@@ -378,7 +392,8 @@ def main():
             cpu = cpu_baseline(os.cpu_count() or 1)
         line = {
             "metric": "auto_compress_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": dt / args.steps * 1e3,
+            "device_ms_per_step": dev_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 (stats/poly/rle/error) + f32 (fft, as the reference)",
             "data": "synthetic", "config": workload_config(S, world),
             "e2e": {"value": e2e_v, "unit": "Msamples/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h},

@@ -168,6 +168,10 @@ int64_t atsc_csv_read_values(const char *text, uint64_t len, int has_header, con
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t atsc_gpu_launch_count(const atsc_ctx *ctx);
 
+/* device time (ms, CUDA events on the library's own streams) of the last compress / decompress call:
+ * from the first operation issued to the last one completed, copies included; max over devices */
+double atsc_gpu_last_call_ms(const atsc_ctx *ctx);
+
 /* CUDA-event time (ms, summed over devices, accumulated since the last reset) of each kernel
  * on the library's own streams: [0] stats [1] plan+polynomial [2] rle [3] fft
  * [4] noop-size+select+scan [5] emit [6] decode [7] host time spent preparing and launching waves */
