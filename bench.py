@@ -79,6 +79,8 @@ class ClockSampler:
             pynvml.nvmlInit()
             self.nvml = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)  # first call is slow: not inside the timed region
         except Exception:
             self.nvml = None
 
@@ -90,8 +92,7 @@ class ClockSampler:
                 "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
         get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
             getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
-        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
-        while not self.stop:
+        while True:
             try:
                 self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
                 r = int(get_reasons(self.h))
@@ -100,6 +101,8 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
+            if self.stop:  # at least one sample, taken while the region is still open
+                break
             time.sleep(0.002)
 
     def _run_smi(self):
