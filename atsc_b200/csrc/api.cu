@@ -94,7 +94,7 @@ struct Engine {
 struct Device {
     int id = 0;
     cudaStream_t st = nullptr;  // setup stream (tables)
-    int n_engines = 0;
+    int n_engines = 0, sms = 0;
     Engine eng[MAX_ENGINES];
     uint64_t wave_samples = 0;
     double *inv_d2 = nullptr;
@@ -329,6 +329,7 @@ int sync_geoms(Device &D) {
 
 // ---------------------------------------------------------------- device setup
 int engine_init(Device &D, Engine &E, int sms) {
+    if (E.st) return ATSC_OK;  // already set up
     CK(cudaStreamCreateWithFlags(&E.st, cudaStreamNonBlocking));
     SlotPool &P = E.pool;
     P.rle_slots = 2 * sms;
@@ -385,8 +386,8 @@ int device_init(Device &D) {
     // waves in flight per device and samples per wave (tunable for experiments)
     D.n_engines = env_int("ATSC_ENGINES", 4, 1, MAX_ENGINES);
     D.wave_samples = (uint64_t)env_int("ATSC_WAVE_MI", 72, 1, 512) << 20;
-    for (int e = 0; e < D.n_engines; e++)
-        if ((rc = engine_init(D, D.eng[e], sms))) return rc;
+    D.sms = sms;
+    if ((rc = engine_init(D, D.eng[0], sms))) return rc;  // the others are set up when a call first needs them
     CK(cudaEventCreate(&D.ev_begin));
     for (int e = 0; e < D.n_engines; e++) CK(cudaEventCreate(&D.ev_end[e]));
     CK(cudaMalloc((void **)&D.geoms_dev, GEOM_CAP * sizeof(FftGeom)));
@@ -441,9 +442,11 @@ int span_begin(Device &D) {
     return ATSC_OK;
 }
 int span_end(Device &D) {
-    for (int k = 0; k < D.n_engines; k++) CK(cudaEventRecord(D.ev_end[k], D.eng[k].st));
     double ms = 0.0;
+    for (int k = 0; k < D.n_engines; k++)
+        if (D.eng[k].st) CK(cudaEventRecord(D.ev_end[k], D.eng[k].st));
     for (int k = 0; k < D.n_engines; k++) {
+        if (!D.eng[k].st) continue;  // engine never reached by a call yet
         CK(cudaStreamSynchronize(D.eng[k].st));
         float t = 0.f;
         CK(cudaEventElapsedTime(&t, D.ev_begin, D.ev_end[k]));
@@ -690,6 +693,7 @@ int compress_on_device(Device &D, const double *samples, bool dev_ptr, const uin
         const uint32_t n = end - pos;
         Engine &E = D.eng[wave % D.n_engines];
         wave++;
+        if ((rc = engine_init(D, E, D.sms))) break;  // ~3.4 GB of workspaces, only for engines a call reaches
         // the engine's previous wave must be collected before its buffers are reused; waves are
         // collected in issue order, so payloads land in frame order
         if ((rc = collect_wave(D, E, idx, out, sink))) break;
@@ -826,6 +830,7 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
         }
         Engine &E = D.eng[wave % D.n_engines];
         wave++;
+        if ((rc = engine_init(D, E, D.sms))) break;
         if ((rc = collect_decode(D, E, idx))) break;
         size_t hc = E.dec_cap;
         if ((rc = grow(D, E.st, E.d_dec, E.dec_cap, n))) break;
