@@ -32,6 +32,7 @@ __device__ inline int fft_slot() { return (threadIdx.x >> 5) * FFT_SUB + ((threa
 constexpr int FFT_KCAP = 16384;                                 // max list entries when compressing (pow2 for the sort)
 constexpr int FFT_DEC_KCAP = 65536;                             // max entries accepted when decoding (pos is a u16)
 constexpr int FFT_SCHED = 23;                                   // fft.rs:348-352
+constexpr int TOPK_U = 16;                                      // key loads in flight per thread in the top-k passes
 
 // one Stockham stage of a sub-FFT: everything the inner loop needs, computed on the host so
 // the kernel does no integer division
@@ -432,7 +433,14 @@ __device__ inline unsigned long long fft_composite(uint32_t key, uint32_t bin) {
 // number of bins with a non-zero |z| (fft_trim stops at the first exact zero, fft.rs:249-252)
 __device__ inline uint32_t fft_count_nonzero(uint32_t Bn, FftWs ws, uint32_t *sh) {
     uint32_t zeros = 0;
-    for (uint32_t b = threadIdx.x; b < Bn; b += blockDim.x) zeros += ws.keys[b] == 0u;
+    constexpr int U = 16;  // loads in flight per thread: the passes over the keys are latency bound
+    for (uint32_t b0 = threadIdx.x; b0 < Bn; b0 += U * blockDim.x) {
+        uint32_t k[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) k[u] = (b0 + u * blockDim.x < Bn) ? ws.keys[b0 + u * blockDim.x] : 1u;
+#pragma unroll
+        for (int u = 0; u < U; u++) zeros += k[u] == 0u;
+    }
     return Bn - block_sum_u32(zeros, sh);
 }
 
@@ -465,12 +473,12 @@ __device__ inline bool fft_topk_chunk(uint32_t Bn, FftWs ws, uint32_t done, uint
         shift = shifts[lv];
         for (uint32_t i = t; i < nbins; i += T) hist[i] = 0;
         __syncthreads();
-        for (uint32_t b0 = t; b0 < Bn; b0 += 4 * T) {
-            uint32_t k[4];
+        for (uint32_t b0 = t; b0 < Bn; b0 += TOPK_U * T) {
+            uint32_t k[TOPK_U];
 #pragma unroll
-            for (int u = 0; u < 4; u++) k[u] = (b0 + u * T < Bn) ? ws.keys[b0 + u * T] : 0u;
+            for (int u = 0; u < TOPK_U; u++) k[u] = (b0 + u * T < Bn) ? ws.keys[b0 + u * T] : 0u;
 #pragma unroll
-            for (int u = 0; u < 4; u++)
+            for (int u = 0; u < TOPK_U; u++)
                 if (k[u] != 0u) {
                     uint32_t bin = shift < 20 ? fft_bin_of(b0 + u * T, pM, pM1, pM2) : 0u;
                     unsigned long long c = fft_composite(k[u], bin);
@@ -494,12 +502,12 @@ __device__ inline bool fft_topk_chunk(uint32_t Bn, FftWs ws, uint32_t done, uint
     __syncthreads();
     if (t == 0) sh[107] = 0;
     __syncthreads();
-    for (uint32_t b0 = t; b0 < Bn; b0 += 4 * T) {
-        uint32_t k[4];
+    for (uint32_t b0 = t; b0 < Bn; b0 += TOPK_U * T) {
+        uint32_t k[TOPK_U];
 #pragma unroll
-        for (int u = 0; u < 4; u++) k[u] = (b0 + u * T < Bn) ? ws.keys[b0 + u * T] : 0u;
+        for (int u = 0; u < TOPK_U; u++) k[u] = (b0 + u * T < Bn) ? ws.keys[b0 + u * T] : 0u;
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int u = 0; u < TOPK_U; u++)
             if (k[u] != 0u) {
                 unsigned long long c = fft_composite(k[u], fft_bin_of(b0 + u * T, pM, pM1, pM2));
                 if (c >= Tlow && c < Cprev) {

@@ -350,16 +350,23 @@ def main():
         traffic = tj.get("k_" + dom)
     except Exception:
         pass
+    alg = {"stats": n_samples * 8, "poly": fft_samples * 8, "fft": fft_samples * 8}
+    one_engine = None
+    if iso and "error" not in iso:
+        one_engine = {"k_" + k: {"ms_per_step": round(iso[k], 4), "achieved": alg[k] / (iso[k] * 1e-3) / 1e9,
+                                 "frac": alg[k] / (iso[k] * 1e-3) / 1e9 / peak}
+                      for k in alg if iso.get(k)}
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic,
+                "frac": achieved / peak, "traffic": traffic, "one_engine": one_engine,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_step": dom_samples * 8,
                 "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items() if v},
                 "kernel_ms_per_step_one_engine": iso,
                 "whole_step_frac": n_samples * 8 / (dt / args.steps) / 1e9 / peak,
-                "note": "kernel_ms_per_step: CUDA events on each engine's stream inside the timed region (waves of "
-                        "several engines overlap, so the durations include contention and add up to more than the "
-                        "step); k_poly is FP64-latency bound, k_fft_fwd FP32/shared-memory bound, k_stats issue "
+                "note": "achieved / frac / kernel_ms_per_step: CUDA events on each engine's stream inside the timed region "
+                        "(waves of several engines overlap, so these durations include contention and add up to more "
+                        "than the step); one_engine: the same kernels with a single engine, i.e. each launch alone on "
+                        "the GPU, which is the figure to hold against the kernel's own roofline; k_poly is FP64-latency bound, k_fft_fwd FP32/shared-memory bound, k_stats issue "
                         "bound (DESIGN.md section 4); the HBM line is the task's stated denominator"}
 
     # ---- decompression of the fleet just produced (device-resident output)
