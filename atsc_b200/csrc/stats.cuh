@@ -43,16 +43,20 @@ struct StatsAcc {
 // scales `ends`); RUNS = false: value part only.
 template <bool UNIFORM, bool RUNS = true>
 __device__ __forceinline__ void stats_sample(StatsAcc &a, double val, double nx, uint32_t i1) {
-    const int hi = __double2hiint(val), lo = __double2loint(val);
+    const int hi = __double2hiint(val);
     if (!(a.flags & 1u)) {
-        // fractional (split_n): for 2^-64 <= |x| < 2^52 exactly "x has a fractional part"; NaN / inf /
-        // integers >= 2^52 / zero: no; the sliver 0 < |x| < 2^-64 is settled by finish_stats
-        const bool ne = val != trunc(val);
-        const uint32_t ef = (uint32_t)hi & 0x7FF00000u;
-        if (ne && (ef - 0x3BF00000u) < 0x44000000u) a.flags |= 1u;
-        if (ne && ef < 0x3BF00000u) a.flags |= 4u;
+        // fractional (split_n): r = (x + copysign(2^52, x)) - copysign(2^52, x) is x rounded to an integer
+        // for |x| < 2^52 and x itself beyond (integers, inf), so "r <> x" (ordered: NaN is not
+        // fractional) is exactly "x has a fractional part"; the sliver 0 < |x| < 2^-64, which split_n
+        // does not call fractional, is settled by finish_stats
+        const double magic = __hiloint2double((hi & (int)0x80000000) | 0x43300000, 0);
+        const double r = __dsub_rn(__dadd_rn(val, magic), magic);
+        if (r < val || r > val) {
+            const uint32_t ef = (uint32_t)hi & 0x7FF00000u;
+            a.flags |= ef >= 0x3BF00000u ? 1u : 4u;
+        }
     }
-    if (lo == 0 && hi == (int)0x80000000) a.flags |= 2u;
+    if (hi == (int)0x80000000 && __double2loint(val) == 0) a.flags |= 2u;
     // strict comparisons: NaN never wins (optimizer/utils.rs:57-64); the sign of a zero extreme is
     // settled afterwards (finish_stats)
     if (val < a.mn) a.mn = val;
