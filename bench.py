@@ -344,10 +344,16 @@ def main():
         iso = {"error": str(ex)}
     finally:
         os.environ.pop("ATSC_ENGINES", None)
-    traffic = None
+    # dram__bytes_read + dram__bytes_write of one launch of the dominant kernel, from the committed
+    # ncu --set full capture (profiles/traffic.json): that launch is one 96-series wave, whose
+    # algorithmic bytes are stated beside it
+    traffic, traffic_detail = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get("k_" + dom)
+        traffic_detail = tj.get("k_" + dom)
+        if traffic_detail:
+            traffic = traffic_detail["bytes_per_launch"]
+            traffic_detail = dict(traffic_detail, algorithmic_bytes_of_that_launch=(96 if dom == "stats" else 64) * SERIES_LEN * 8)
     except Exception:
         pass
     alg = {"stats": n_samples * 8, "poly": fft_samples * 8, "fft": fft_samples * 8}
@@ -357,7 +363,7 @@ def main():
                                  "frac": alg[k] / (iso[k] * 1e-3) / 1e9 / peak}
                       for k in alg if iso.get(k)}
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "one_engine": one_engine,
+                "frac": achieved / peak, "traffic": traffic, "traffic_detail": traffic_detail, "one_engine": one_engine,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_step": dom_samples * 8,
                 "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items() if v},
