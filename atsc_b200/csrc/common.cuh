@@ -218,8 +218,9 @@ __device__ __forceinline__ double div_1e5(double n) {
 __device__ __forceinline__ double rcp_fast(double o) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(o));
+    // seed +-inf (o zero / denormal), 0 (o = +-inf) or NaN all turn the Newton step into NaN: keep the seed
     const double y1 = __fma_rn(y, __fma_rn(-o, y, 1.0), y);
-    return (y1 == y1 && fabs(y) != __longlong_as_double(0x7FF0000000000000ll) && y != 0.0) ? y1 : y;
+    return y1 == y1 ? y1 : y;
 }
 // One MAPE term |(out - o) / o| (utils/error.rs:110-113) through a reciprocal good to ~3e-14
 // relative (absorbed by the near-tie tolerance, the error only feeds threshold tests); an exactly
