@@ -9,6 +9,7 @@
 
 #include <charconv>
 #include <cmath>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -97,6 +98,8 @@ int compress_series(atsc_ctx *ctx, const std::vector<double> &data, const Args &
     return 0;
 }
 
+bool load_series(const std::string &path, const Args &a, std::vector<double> &data);
+
 int process_single_file(atsc_ctx *ctx, const std::string &path, const Args &a) {
     std::vector<uint8_t> file;
     if (a.uncompress) {
@@ -128,9 +131,23 @@ int process_single_file(atsc_ctx *ctx, const std::string &path, const Args &a) {
         return write_file(with_extension(path, "wbro"), w.data(), w.size()) ? 0 : 1;
     }
     std::vector<double> data;
+    if (!load_series(path, a, data)) return 1;
+    if (a.verbose) print_vec("Input", data);
+    std::vector<uint8_t> bro;
+    int rc = compress_series(ctx, data, a, bro);
+    if (rc) {
+        fprintf(stderr, "compress failed (%d): %s\n", rc, atsc_gpu_last_error(ctx));
+        return 1;
+    }
+    return write_file(with_extension(path, "bro"), bro.data(), bro.size()) ? 0 : 1;
+}
+
+// reads one input file of a compression run into `data`; returns false (after reporting) on failure
+bool load_series(const std::string &path, const Args &a, std::vector<double> &data) {
+    std::vector<uint8_t> file;
     if (!read_file(path, file)) {
         fprintf(stderr, "cannot open %s\n", path.c_str());
-        return 1;
+        return false;
     }
     if (a.csv) {
         std::string tf = "time", vf = "value";
@@ -144,7 +161,7 @@ int process_single_file(atsc_ctx *ctx, const std::string &path, const Args &a) {
         if (n < 0) {
             const char *msg = n == -1 ? "Timestamp field is not found" : n == -2 ? "Value field is not found" : "Parsing value is failed";
             fprintf(stderr, "%s File: %s\n", msg, path.c_str());
-            return 1;
+            return false;
         }
         data.resize((size_t)n);
         atsc_csv_read_values((const char *)file.data(), file.size(), a.no_header ? 0 : 1, tf.c_str(), vf.c_str(), data.data(),
@@ -153,24 +170,19 @@ int process_single_file(atsc_ctx *ctx, const std::string &path, const Args &a) {
         int64_t n = atsc_wbro_decode(file.data(), file.size(), nullptr, 0);
         if (n < 0) {
             fprintf(stderr, "Ill-formed WAVBRRO file File: %s\n", path.c_str());
-            return 1;
+            return false;
         }
         data.resize((size_t)n);
         atsc_wbro_decode(file.data(), file.size(), data.data(), data.size());
     }
-    if (a.verbose) print_vec("Input", data);
-    std::vector<uint8_t> bro;
-    int rc = compress_series(ctx, data, a, bro);
-    if (rc) {
-        fprintf(stderr, "compress failed (%d): %s\n", rc, atsc_gpu_last_error(ctx));
-        return 1;
-    }
-    return write_file(with_extension(path, "bro"), bro.data(), bro.size()) ? 0 : 1;
+    return true;
 }
 
+// Fleet driver (main.rs:50-68).  The reference walks read_dir lazily, processes every
+// file twice and picks up the files it writes on the way; here the listing is taken once and the
+// files go to the GPU in BATCHES (up to ~256 Mi samples or 4096 files per call), so the wave
+// pipeline of the library sees whole fleets instead of one series at a time.
 int process_directory(atsc_ctx *ctx, const Args &a) {
-    // main.rs:50-68 walks read_dir lazily and processes every file twice, picking up the files it
-    // writes on the way; here the listing is taken once, each file processed once.
     DIR *d = opendir(a.input.c_str());
     if (!d) return 1;
     std::vector<std::string> files;
@@ -180,10 +192,96 @@ int process_directory(atsc_ctx *ctx, const Args &a) {
         if (stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode)) files.push_back(p);
     }
     closedir(d);
-    int rc = 0;
-    for (auto &f : files)
-        if (process_single_file(ctx, f, a)) rc = 1;
-    return rc;
+    std::sort(files.begin(), files.end());
+    int ret = 0;
+    const uint64_t BATCH_SAMPLES = 256ull << 20;
+    const size_t BATCH_FILES = 4096;
+    if (a.uncompress) {
+        size_t i = 0;
+        while (i < files.size()) {
+            std::vector<uint8_t> blob;
+            std::vector<uint64_t> off, len;
+            std::vector<std::string> names;
+            while (i < files.size() && names.size() < BATCH_FILES && blob.size() < (1ull << 30)) {
+                std::vector<uint8_t> file;
+                const std::string &path = files[i++];
+                if (!read_file(path, file)) {
+                    ret = 1;
+                    continue;
+                }
+                if (file.size() < 12) {  // bro_reader.rs:41-43
+                    fprintf(stderr, "failed to fill whole buffer File: %s\n", path.c_str());
+                    ret = 1;
+                    continue;
+                }
+                if (memcmp(file.data(), "BRRO", 4) != 0) continue;  // not a BRO file: silently skipped
+                off.push_back(blob.size());
+                len.push_back(file.size());
+                names.push_back(path);
+                blob.insert(blob.end(), file.begin(), file.end());
+            }
+            const uint32_t n = (uint32_t)names.size();
+            if (!n) continue;
+            std::vector<uint64_t> count(n), ooff(n);
+            int rc = atsc_gpu_decompress_series(ctx, blob.data(), off.data(), len.data(), n, nullptr, nullptr, count.data());
+            uint64_t total = 0;
+            for (uint32_t s = 0; s < n; s++) {
+                ooff[s] = total;
+                total += count[s];
+            }
+            std::vector<double> out((size_t)total + 1);
+            if (!rc && total)
+                rc = atsc_gpu_decompress_series(ctx, blob.data(), off.data(), len.data(), n, out.data(), ooff.data(), count.data());
+            if (rc) {
+                fprintf(stderr, "decompress failed (%d): %s\n", rc, atsc_gpu_last_error(ctx));
+                ret = 1;
+                continue;
+            }
+            for (uint32_t s = 0; s < n; s++) {
+                const double *p = out.data() + ooff[s];
+                if (a.verbose) print_vec("Output", std::vector<double>(p, p + count[s]));
+                std::vector<uint8_t> w(atsc_wbro_encode(p, count[s], nullptr, 0));
+                atsc_wbro_encode(p, count[s], w.data(), w.size());
+                if (!write_file(with_extension(names[s], "wbro"), w.data(), w.size())) ret = 1;
+            }
+        }
+        return ret;
+    }
+    size_t i = 0;
+    while (i < files.size()) {
+        std::vector<double> samples;
+        std::vector<uint64_t> off, len;
+        std::vector<std::string> names;
+        while (i < files.size() && names.size() < BATCH_FILES && samples.size() < BATCH_SAMPLES) {
+            std::vector<double> data;
+            const std::string &path = files[i++];
+            if (!load_series(path, a, data)) {
+                ret = 1;
+                continue;
+            }
+            if (a.verbose) print_vec("Input", data);
+            off.push_back(samples.size());
+            len.push_back(data.size());
+            names.push_back(path);
+            samples.insert(samples.end(), data.begin(), data.end());
+        }
+        const uint32_t n = (uint32_t)names.size();
+        if (!n) continue;
+        std::vector<uint8_t> bro(samples.size() * 16 + 4096 * (size_t)n + 64 * (samples.size() / 512 + 8 * (size_t)n));
+        std::vector<uint64_t> boff(n), blen(n);
+        double dummy = 0.0;
+        int rc = atsc_gpu_compress_series(ctx, samples.empty() ? &dummy : samples.data(), off.data(), len.data(), n,
+                                          (uint8_t)a.compressor, a.error, a.speed, bro.data(), bro.size(), boff.data(),
+                                          blen.data(), nullptr);
+        if (rc) {
+            fprintf(stderr, "compress failed (%d): %s\n", rc, atsc_gpu_last_error(ctx));
+            ret = 1;
+            continue;
+        }
+        for (uint32_t s = 0; s < n; s++)
+            if (!write_file(with_extension(names[s], "bro"), bro.data() + boff[s], (size_t)blen[s])) ret = 1;
+    }
+    return ret;
 }
 
 int usage() {

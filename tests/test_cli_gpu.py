@@ -86,3 +86,37 @@ def test_cli_csv_and_verbose(tmp_path):
     q.write_text("".join(f"{float(v)!r}\n" for v in vals))
     run("--csv", "--no-header", "--compressor", "noop", str(q))
     assert open(q.with_suffix(".bro"), "rb").read() == open(p.with_suffix(".bro"), "rb").read()
+
+
+def test_cli_directory_fleet(tmp_path):
+    """main.rs:50-68 directory mode: every file of a directory, batched into one GPU call; each
+    .bro equals what the single-file path (and the oracle) produces, and -u on the directory
+    restores every series."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import atsc_b200
+    import gen
+    d = tmp_path / "fleet"
+    d.mkdir()
+    kinds = ["constant", "gauge", "util", "saw", "steps", "periodic"]
+    series = {}
+    for i, k in enumerate(kinds * 2):
+        x = gen.make(k, 3000 + 517 * i, 40 + i)
+        series[f"s{i:02d}"] = x
+        (d / f"s{i:02d}.wbro").write_bytes(atsc_b200.wbro_encode(x))
+    run("--compressor", "auto", "-e", "5", str(d))
+    for name, x in series.items():
+        bro = (d / f"{name}.bro").read_bytes()
+        want, comps = O.compress_stream(x, compressor=O.AUTO, error_pct=5)
+        if O.FFT not in comps:
+            assert bro == want, name
+        else:
+            assert len(O.decompress_stream(bro)) == len(x)
+        os.remove(d / f"{name}.wbro")
+    run("-u", str(d))
+    for name, x in series.items():
+        got = atsc_b200.wbro_decode((d / f"{name}.wbro").read_bytes())
+        assert len(got) == len(x)
+        nz = x != 0
+        assert O.mape(x[nz], got[nz]) <= 0.0505, name
