@@ -29,7 +29,8 @@ API_SYMBOLS = [
     "atsc_gpu_compress_series", "atsc_gpu_decompress_series", "atsc_gpu_launch_count", "atsc_gpu_kernel_ms",
     "atsc_plan_shards", "atsc_wbro_decode", "atsc_wbro_encode", "atsc_csv_read_values", "atsc_gpu_last_call_ms",
 ]
-KERNEL_NAMES = ["stats", "poly", "rle", "fft", "select", "emit", "decode", "host_issue"]
+KERNEL_NAMES = ["stats", "poly", "rle", "fft_fwd", "select", "emit", "decode", "host_issue", "fft_small", "fft",
+                "reserved10", "reserved11"]
 
 
 class AtscError(RuntimeError):
@@ -210,7 +211,7 @@ class Context:
 
     def kernel_ms(self, reset=True):
         """CUDA-event milliseconds per kernel since the last reset (dict by kernel name)."""
-        arr = (C.c_double * 8)()
+        arr = (C.c_double * 12)()
         self.L.atsc_gpu_kernel_ms(self.h, arr, 1 if reset else 0)
         return {k: arr[i] for i, k in enumerate(KERNEL_NAMES)}
 

@@ -85,7 +85,7 @@ struct Engine {
     uint32_t *d_status = nullptr, *h_status = nullptr;
     size_t status_cap = 0;
     // CUDA events around every kernel of the wave (kernel_ms)
-    cudaEvent_t ev[10] = {};
+    cudaEvent_t ev[12] = {};  // 0-7 compress pipeline, 8-9 decode, 10-11 between the FFT kernels
     WaveJob job;
     bool dec_active = false;  // a decode wave is pending on this engine
     uint32_t dec_pos = 0, dec_n = 0;
@@ -110,9 +110,10 @@ struct Device {
     cudaEvent_t ev_begin = nullptr, ev_end[MAX_ENGINES] = {};
     double last_call_ms = 0.0;
     // CUDA-event time of every kernel (ms accumulated since reset):
-    // 0 stats, 1 plan+poly, 2 rle, 3 fft_small+fft_fwd+fft, 4 noop+select+scan, 5 emit, 6 decode,
-    // 7 HOST time spent preparing and launching waves (not a kernel: shows when a call is host bound)
-    double ms[8] = {};
+    // 0 stats, 1 plan+poly, 2 rle, 3 fft_fwd, 4 noop+select+scan, 5 emit, 6 decode,
+    // 7 HOST time spent preparing and launching waves (not a kernel: shows when a call is host bound),
+    // 8 fft_small, 9 fft (top-k + refinement loop)
+    double ms[12] = {};
     std::string err;
 };
 
@@ -550,10 +551,12 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
         launch_fft_small(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.d_arena, small_lmax, E.queues + 8, st);
         D.launches++;
     }
+    CK(cudaEventRecord(E.ev[10], st));
     if (spec) {
         launch_fft_fwd(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_spec_xd, E.d_spec_keys, E.queues + 7, st);
         D.launches++;
     }
+    CK(cudaEventRecord(E.ev[11], st));
     if (any_large) {
         launch_fft(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_arena, E.d_spec_xd, E.d_spec_keys, E.queues + 3, st);
         D.launches++;
@@ -587,10 +590,14 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
 int wait_wave(Device &D, Engine &E, uint32_t n, const double *d_samples, uint64_t *payload_total) {
     CK(cudaStreamSynchronize(E.st));
     CK(cudaGetLastError());
-    for (int k = 0; k < 5; k++) {
-        float t = 0.f;
-        CK(cudaEventElapsedTime(&t, E.ev[k], E.ev[k + 1]));
-        D.ms[k == 2 ? 3 : k == 3 ? 2 : k] += t;  // the FFT kernels run before k_rle
+    {
+        // stream order: stats | plan+poly | fft_small | fft_fwd | fft | rle | noop+select+scan
+        const int a[7] = {0, 1, 2, 10, 11, 3, 4}, b[7] = {1, 2, 10, 11, 3, 4, 5}, slot[7] = {0, 1, 8, 3, 9, 2, 4};
+        for (int k = 0; k < 7; k++) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, E.ev[a[k]], E.ev[b[k]]));
+            D.ms[slot[k]] += t;
+        }
     }
     float te = 0.f;
     CK(cudaEventElapsedTime(&te, E.ev[6], E.ev[7]));
@@ -984,11 +991,12 @@ double atsc_gpu_last_call_ms(const atsc_ctx *ctx) {
     return ms;
 }
 
-void atsc_gpu_kernel_ms(atsc_ctx *ctx, double *out8, int reset) {
-    for (int k = 0; k < 8; k++) out8[k] = 0.0;
+void atsc_gpu_kernel_ms(atsc_ctx *ctx, double *out12, int reset) {
+    double *out8 = out12;
+    for (int k = 0; k < 12; k++) out8[k] = 0.0;
     if (!ctx) return;
     for (Device *D : ctx->devs)
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < 12; k++) {
             out8[k] += D->ms[k];
             if (reset) D->ms[k] = 0.0;
         }

@@ -173,9 +173,10 @@ uint64_t atsc_gpu_launch_count(const atsc_ctx *ctx);
 double atsc_gpu_last_call_ms(const atsc_ctx *ctx);
 
 /* CUDA-event time (ms, summed over devices, accumulated since the last reset) of each kernel
- * on the library's own streams: [0] stats [1] plan+polynomial [2] rle [3] fft
- * [4] noop-size+select+scan [5] emit [6] decode [7] host time spent preparing and launching waves */
-void atsc_gpu_kernel_ms(atsc_ctx *ctx, double *out8, int reset);
+ * on the library's own streams, 12 slots: [0] stats [1] plan+polynomial [2] rle [3] fft_fwd
+ * [4] noop-size+select+scan [5] emit [6] decode [7] host time spent preparing and launching waves
+ * [8] fft_small [9] fft (top-k + refinement loop) [10..11] reserved */
+void atsc_gpu_kernel_ms(atsc_ctx *ctx, double *out12, int reset);
 
 #ifdef __cplusplus
 }
