@@ -157,21 +157,20 @@ __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys 
         const uint32_t i_hi = K - 3;  // inclusive; keys i and i+1 are regular for every i <= K-3
         // two segments per trip: their (long, strictly serial) f64 chains are independent, and with
         // every helper branch free the compiler interleaves them
-        for (uint32_t i = 1 + g; i <= i_hi; i += 2 * G) {
-            const uint32_t i2 = i + G;
-            const bool two = i2 <= i_hi;
-            const uint32_t xa = i * step, xb = (two ? i2 : i) * step;
+        auto seg_err = [&](uint32_t i) -> double {
+            const uint32_t xa = i * step;
             const double o = d[xa + j], av = d[xa], bv = d[xa + step], ta = tang[i], tb = tang[i + 1];
-            const double o2 = d[xb + j], av2 = d[xb], bv2 = d[xb + step], ta2 = tang[two ? i2 : i], tb2 = tang[(two ? i2 : i) + 1];
             const double v = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(av, h00), __dmul_rn(ta, h10)), __dmul_rn(bv, h01)),
                                        __dmul_rn(tb, h11));
-            const double v2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(av2, h00), __dmul_rn(ta2, h10)), __dmul_rn(bv2, h01)),
-                                        __dmul_rn(tb2, h11));
-            const double e1 = mape_term(round_and_limit5_fast(v, vmin, vmax), o);
-            const double e2 = mape_term(round_and_limit5_fast(v2, vmin, vmax), o2);
+            return mape_term(round_and_limit5_fast(v, vmin, vmax), o);
+        };
+        uint32_t i = 1 + g;
+        for (; i + G <= i_hi; i += 2 * G) {  // both segments of the trip exist
+            const double e1 = seg_err(i), e2 = seg_err(i + G);
             acc += e1;
-            if (two) acc += e2;
+            acc += e2;
         }
+        if (i <= i_hi) acc += seg_err(i);
     }
     // ---- the Linear ends: segment 0, segment K-2 (possibly irregular) and the last sample
     const uint32_t Kreg = k.Kreg;
