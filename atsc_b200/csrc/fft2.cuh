@@ -138,7 +138,7 @@ struct DftS<27, S, INV> {
 __device__ __forceinline__ float2 f2_load_z(const double *__restrict__ d, int N, int prefix, int n, bool vec) {
     int i0 = 2 * n - prefix, i1 = i0 + 1;
     if (vec && i0 >= 0 && i1 < N) {
-        const double2 v = __ldg(reinterpret_cast<const double2 *>(d + i0));
+        const double2 v = __ldcs(reinterpret_cast<const double2 *>(d + i0));  // last use of the frame in this wave
         return make_float2((float)v.x, (float)v.y);
     }
     i0 = min(max(i0, 0), N - 1);

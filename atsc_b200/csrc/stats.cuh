@@ -96,7 +96,7 @@ __device__ __forceinline__ void chunk_scan(StatsAcc &a, const double *__restrict
         for (; p0 < Pfull; p0 += U * T) {  // every pair of the tile exists and has a successor pair or dc[2P]
             double2 v[U];
 #pragma unroll
-            for (uint32_t u = 0; u < U; u++) v[u] = __ldg(d2 + p0 + u * T + t);
+            for (uint32_t u = 0; u < U; u++) v[u] = __ldcs(d2 + p0 + u * T + t);  // streamed once: do not keep in L1 / L2
 #pragma unroll
             for (uint32_t u = 0; u < U; u++) {
                 const uint32_t p = p0 + u * T + t;
