@@ -99,7 +99,7 @@ __global__ void k_plan(FrameWork *fr, uint32_t n, const double *__restrict__ sam
 // =========================================================================================
 // polynomial / idw
 // =========================================================================================
-__global__ void __launch_bounds__(BLOCK) k_poly(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
+__global__ void __launch_bounds__(512, 2) k_poly(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
                                                 double max_err, const double *__restrict__ inv_d2, SlotPool pool,
                                                 unsigned *q) {
     __shared__ double shd[64];
@@ -1130,7 +1130,7 @@ void launch_plan(FrameWork *fr, uint32_t n, const double *samples, const StatsPa
 }
 void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_err, const double *inv_d2,
                  SlotPool pool, unsigned *q, cudaStream_t st) {
-    k_poly<<<grid_for(n, pool.poly_slots), BLOCK, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);
+    k_poly<<<grid_for(n, pool.poly_slots), 512, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);
 }
 void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err, SlotPool pool, unsigned *q,
                 cudaStream_t st) {
