@@ -40,7 +40,7 @@ __device__ inline FftWs fft_slot(const SlotPool &p, int s) {
 // =========================================================================================
 // stats
 // =========================================================================================
-__global__ void __launch_bounds__(512, 4) k_stats(const FrameWork *__restrict__ fr, const ChunkRef *__restrict__ chunks,
+__global__ void __launch_bounds__(256, 8) k_stats(const FrameWork *__restrict__ fr, const ChunkRef *__restrict__ chunks,
                                                     uint32_t n_chunks, const double *__restrict__ samples,
                                                     StatsPart *parts, unsigned *q) {
     __shared__ StatsSmem sm;
@@ -1123,7 +1123,7 @@ static inline int grid_for(uint32_t n, int slots) { return (int)(n < (uint32_t)s
 
 void launch_stats(const FrameWork *fr, const ChunkRef *chunks, uint32_t n_chunks, const double *samples, StatsPart *parts,
                   unsigned *q, cudaStream_t st) {
-    k_stats<<<grid_for(n_chunks, 4 * sms()), 512, 0, st>>>(fr, chunks, n_chunks, samples, parts, q);
+    k_stats<<<grid_for(n_chunks, 8 * sms()), 256, 0, st>>>(fr, chunks, n_chunks, samples, parts, q);
 }
 void launch_plan(FrameWork *fr, uint32_t n, const double *samples, const StatsPart *parts, cudaStream_t st) {
     k_plan<<<(n + 63) / 64, 64, 0, st>>>(fr, n, samples, parts);
