@@ -29,7 +29,7 @@ using namespace atsc;
 namespace {
 
 constexpr uint32_t WAVE_FRAMES = 1u << 18;
-constexpr int MAX_ENGINES = 4;
+constexpr int MAX_ENGINES = 8;
 constexpr size_t GEOM_CAP = 512;  // distinct transform lengths 2^a 3^b <= 139968 (about 120 exist)
 
 struct FrameReq {
