@@ -814,7 +814,8 @@ __device__ uint32_t dec_noop(const uint8_t *__restrict__ p, uint32_t len, uint32
 }
 
 __device__ uint32_t dec_poly(const uint8_t *__restrict__ p, uint32_t len, uint32_t N, double *out, double *pts,
-                             double *tang, const double *__restrict__ inv_d2, DecShared *ds, uint32_t *sh) {
+                             double *tang, const double *__restrict__ inv_d2, DecShared *ds, uint32_t *sh,
+                             double *smem, uint32_t smem_cap) {
     const uint32_t T = blockDim.x, t = threadIdx.x;
     if (t == 0) {
         uint32_t bad = 0, hdr = 0, K = 0;
@@ -866,7 +867,7 @@ __device__ uint32_t dec_poly(const uint8_t *__restrict__ p, uint32_t len, uint32
     PolyKeys k = poly_keys(N, step);
     if (K != k.K) return 5;
     if (!ptype) {
-        poly_expand(pts, k, vmin, vmax, tang, out);
+        poly_expand(pts, k, vmin, vmax, tang, out, smem, smem_cap);
         return 0;
     }
     auto pf = [&](uint32_t j) { return pts[j]; };
@@ -1072,7 +1073,10 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_decode(const DecFrame *__res
             case C_CONSTANT: rc = dec_constant(p, f.payload_len, f.sample_count, o, &ds); break;
             case C_NOOP: rc = dec_noop(p, f.payload_len, f.sample_count, o, &ds, sh); break;
             case C_POLY:
-            case C_IDW: rc = dec_poly(p, f.payload_len, f.sample_count, o, pts, tang, inv_d2, &ds, sh); break;
+            case C_IDW:
+                rc = dec_poly(p, f.payload_len, f.sample_count, o, pts, tang, inv_d2, &ds, sh, reinterpret_cast<double *>(dyn_f2),
+                              (uint32_t)(FFT_SMEM_BYTES / sizeof(double)));
+                break;
             case C_RLE: rc = dec_rle(p, f.payload_len, f.sample_count, o, pts, idxs, mark, &ds, sh); break;
             case C_FFT: rc = dec_fft(p, f.payload_len, f.sample_count, o, geoms, f.geom, fws, dyn_f2, &ds, sh, &sg); break;
             default: rc = 4; break;

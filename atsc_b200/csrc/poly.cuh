@@ -208,9 +208,21 @@ __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys 
 // arithmetic as poly_eval_at (same operations, same order; the final quotient by 1e5 is the
 // correctly rounded one, div_1e5), organised like poly_mape: thread t owns one offset inside the
 // segments, tangents come from a pre-pass.  All threads call.
-__device__ inline void poly_expand(const double *__restrict__ pts, const PolyKeys &k, double vmin, double vmax,
-                                   double *__restrict__ tang, double *__restrict__ out) {
+// smem / smem_cap: optional shared-memory scratch (doubles); when the keys and tangents of the frame
+// fit (2 K <= smem_cap, e.g. every 131072-sample frame stored at step >= 25) they are served from
+// there instead of the L2-resident global scratch.
+__device__ inline void poly_expand(const double *__restrict__ pts_g, const PolyKeys &k, double vmin, double vmax,
+                                   double *__restrict__ tang_g, double *__restrict__ out, double *smem = nullptr,
+                                   uint32_t smem_cap = 0) {
     const uint32_t N = k.N, step = k.step, K = k.K, T = blockDim.x, t = threadIdx.x;
+    const double *pts = pts_g;
+    double *tang = tang_g;
+    if (smem && 2u * K <= smem_cap) {
+        for (uint32_t j = t; j < K; j += T) smem[j] = pts_g[j];
+        pts = smem;
+        tang = smem + K;
+        __syncthreads();
+    }
     auto pf = [&](uint32_t j) { return pts[j]; };
     auto fin = [&](double v) {
         double o = div_1e5(round_half_away(__dmul_rn(v, 100000.0)));
