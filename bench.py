@@ -420,7 +420,8 @@ def main():
             "metric": "auto_compress_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": dt / args.steps * 1e3,
             "device_ms_per_step": dev_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (stats/poly/rle/error) + f32 (fft, as the reference)",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32",
+            "dtype_note": "f64 for stats / polynomial / rle / error metrics, f32 for the FFT (Complex<f32> in the reference)",
             "data": "synthetic", "config": workload_config(S, world),
             "e2e": {"value": e2e_v, "unit": "Msamples/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "decompress": dec,
