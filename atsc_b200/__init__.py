@@ -28,6 +28,10 @@ API_SYMBOLS = [
     "atsc_gpu_compress_frames", "atsc_gpu_decompress_frames", "atsc_plan_chunk_sizes",
     "atsc_gpu_compress_series", "atsc_gpu_decompress_series", "atsc_gpu_launch_count", "atsc_gpu_kernel_ms",
     "atsc_plan_shards", "atsc_wbro_decode", "atsc_wbro_encode", "atsc_csv_read_values", "atsc_gpu_last_call_ms",
+    "atsc_vsri_new", "atsc_vsri_free", "atsc_day_elapsed_seconds", "atsc_vsri_update_for_point", "atsc_vsri_min",
+    "atsc_vsri_max", "atsc_vsri_sample_count", "atsc_vsri_segment_count", "atsc_vsri_get_sample", "atsc_vsri_get_time",
+    "atsc_vsri_get_next_sample", "atsc_vsri_get_previous_sample", "atsc_vsri_is_empty", "atsc_vsri_all_timestamps",
+    "atsc_vsri_to_text", "atsc_vsri_from_text",
 ]
 KERNEL_NAMES = ["stats", "poly", "rle", "fft_fwd", "select", "emit", "decode", "host_issue", "fft_small", "fft",
                 "reserved10", "reserved11"]
@@ -89,6 +93,31 @@ def load_library(build_if_missing=True):
     L.atsc_wbro_encode.argtypes = [vp, C.c_uint64, vp, C.c_uint64]
     L.atsc_csv_read_values.restype = C.c_int64
     L.atsc_csv_read_values.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_char_p, C.c_char_p, vp, C.c_uint64]
+    i32p = C.POINTER(C.c_int32)
+    L.atsc_vsri_new.restype = vp
+    L.atsc_vsri_new.argtypes = []
+    L.atsc_vsri_free.restype = None
+    L.atsc_vsri_free.argtypes = [vp]
+    L.atsc_day_elapsed_seconds.restype = C.c_int32
+    L.atsc_day_elapsed_seconds.argtypes = [C.c_int64]
+    L.atsc_vsri_update_for_point.restype = C.c_int
+    L.atsc_vsri_update_for_point.argtypes = [vp, C.c_int32]
+    for nm in ("atsc_vsri_min", "atsc_vsri_max", "atsc_vsri_sample_count"):
+        getattr(L, nm).restype = C.c_int32
+        getattr(L, nm).argtypes = [vp]
+    L.atsc_vsri_segment_count.restype = C.c_uint64
+    L.atsc_vsri_segment_count.argtypes = [vp]
+    for nm in ("atsc_vsri_get_sample", "atsc_vsri_get_time", "atsc_vsri_get_next_sample", "atsc_vsri_get_previous_sample"):
+        getattr(L, nm).restype = C.c_int
+        getattr(L, nm).argtypes = [vp, C.c_int32, i32p]
+    L.atsc_vsri_is_empty.restype = C.c_int
+    L.atsc_vsri_is_empty.argtypes = [vp, C.c_int32, C.c_int32]
+    L.atsc_vsri_all_timestamps.restype = C.c_uint64
+    L.atsc_vsri_all_timestamps.argtypes = [vp, i32p, C.c_uint64]
+    L.atsc_vsri_to_text.restype = C.c_uint64
+    L.atsc_vsri_to_text.argtypes = [vp, C.c_char_p, C.c_uint64]
+    L.atsc_vsri_from_text.restype = vp
+    L.atsc_vsri_from_text.argtypes = [C.c_char_p, C.c_uint64]
     L.atsc_gpu_last_call_ms.restype = C.c_double
     L.atsc_gpu_last_call_ms.argtypes = [vp]
     L.atsc_gpu_kernel_ms.restype = None
@@ -107,6 +136,74 @@ def load_library(build_if_missing=True):
     L.atsc_gpu_decompress_series.argtypes = [vp, vp, u64p, u64p, C.c_uint32, vp, u64p, u64p]
     _lib = L
     return L
+
+
+class Vsri:
+    """vsri::Vsri (vsri/src/lib.rs) through the C ABI; host only."""
+
+    def __init__(self, handle=None):
+        self.L = load_library()
+        self.h = handle if handle is not None else self.L.atsc_vsri_new()
+
+    @classmethod
+    def from_text(cls, text):
+        L = load_library()
+        b = text.encode() if isinstance(text, str) else bytes(text)
+        h = L.atsc_vsri_from_text(b, len(b))
+        if not h:
+            raise ValueError("malformed VSRI text")
+        return cls(h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.atsc_vsri_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def update_for_point(self, y):
+        return self.L.atsc_vsri_update_for_point(self.h, int(y)) == 0
+
+    def _opt(self, fn, a):
+        out = C.c_int32()
+        return int(out.value) if fn(self.h, int(a), C.byref(out)) else None
+
+    def get_sample(self, y):
+        return self._opt(self.L.atsc_vsri_get_sample, y)
+
+    def get_time(self, x):
+        return self._opt(self.L.atsc_vsri_get_time, x)
+
+    def get_next_sample(self, y):
+        return self._opt(self.L.atsc_vsri_get_next_sample, y)
+
+    def get_previous_sample(self, y):
+        return self._opt(self.L.atsc_vsri_get_previous_sample, y)
+
+    def is_empty(self, t0, t1):
+        return bool(self.L.atsc_vsri_is_empty(self.h, int(t0), int(t1)))
+
+    min = property(lambda self: int(self.L.atsc_vsri_min(self.h)))
+    max = property(lambda self: int(self.L.atsc_vsri_max(self.h)))
+    sample_count = property(lambda self: int(self.L.atsc_vsri_sample_count(self.h)))
+    segment_count = property(lambda self: int(self.L.atsc_vsri_segment_count(self.h)))
+
+    def all_timestamps(self):
+        n = self.L.atsc_vsri_all_timestamps(self.h, None, 0)
+        out = (C.c_int32 * max(int(n), 1))()
+        self.L.atsc_vsri_all_timestamps(self.h, out, n)
+        return [int(out[i]) for i in range(n)]
+
+    def to_text(self):
+        n = self.L.atsc_vsri_to_text(self.h, None, 0)
+        buf = C.create_string_buffer(int(n) + 1)
+        self.L.atsc_vsri_to_text(self.h, buf, n)
+        return buf.raw[:n].decode()
+
+
+def day_elapsed_seconds(ts):
+    return int(load_library().atsc_day_elapsed_seconds(int(ts)))
 
 
 def chunk_sizes(n):

@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libatsc_gpu.so")
 CLI = os.path.join(HERE, "atsc")
-SOURCES = ["kernels.cu", "api.cu", "stream.cpp", "ingest.cpp"]
+CSV_CLI = os.path.join(HERE, "csv-compressor")
+SOURCES = ["kernels.cu", "api.cu", "stream.cpp", "ingest.cpp", "vsri.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "-Xcompiler", "-fPIC",
@@ -25,13 +26,13 @@ NVCC_FLAGS = [
 
 def _deps():
     files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    files.append(os.path.join(HERE, "host", "atsc_cli.cpp"))
+    files += [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host"))]
     files.append(os.path.join(os.path.dirname(HERE), "include", "atsc_gpu.h"))
     return files
 
 
 def is_stale():
-    if not os.path.exists(OUT) or not os.path.exists(CLI):
+    if not all(os.path.exists(p) for p in (OUT, CLI, CSV_CLI)):
         return True
     t = os.path.getmtime(OUT)
     return any(os.path.getmtime(f) > t for f in _deps())
@@ -59,9 +60,10 @@ def build(force=False, verbose=False):
     cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.check_call(cmd)
     # the `atsc` command line (reference option surface) on top of the library
-    cli_src = os.path.join(HERE, "host", "atsc_cli.cpp")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", cli_src, "-o", CLI, "-L" + HERE, "-latsc_gpu",
-                           "-Wl,-rpath,$ORIGIN"])
+    # and the `csv-compressor` tool (csv-compressor/src/main.rs)
+    for src, exe in (("atsc_cli.cpp", CLI), ("csv_compressor_cli.cpp", CSV_CLI)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", os.path.join(HERE, "host", src), "-o", exe,
+                               "-L" + HERE, "-latsc_gpu", "-Wl,-rpath,$ORIGIN"])
     return OUT
 
 

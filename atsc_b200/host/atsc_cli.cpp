@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/atsc_gpu.h"
+#include "cli_common.h"
 
 namespace {
 
@@ -33,28 +34,6 @@ struct Args {
     std::string fields = "time,value";
 };
 
-bool read_file(const std::string &path, std::vector<uint8_t> &out) {
-    std::ifstream f(path, std::ios::binary);
-    if (!f) return false;
-    f.seekg(0, std::ios::end);
-    std::streamsize n = f.tellg();
-    f.seekg(0);
-    out.resize((size_t)n);
-    return n == 0 || (bool)f.read((char *)out.data(), n);
-}
-bool write_file(const std::string &path, const uint8_t *p, size_t n) {
-    std::ofstream f(path, std::ios::binary | std::ios::trunc);
-    if (!f) return false;
-    f.write((const char *)p, (std::streamsize)n);
-    return (bool)f;
-}
-// PathBuf::set_extension
-std::string with_extension(const std::string &path, const char *ext) {
-    size_t slash = path.find_last_of('/');
-    size_t dot = path.find_last_of('.');
-    std::string stem = (dot != std::string::npos && (slash == std::string::npos || dot > slash + 1)) ? path.substr(0, dot) : path;
-    return stem + "." + ext;
-}
 // Rust `{:?}` of f64: shortest round-trip digits, always a fractional part or an exponent
 std::string debug_f64(double v) {
     if (std::isnan(v)) return "NaN";

@@ -165,6 +165,28 @@ uint64_t atsc_wbro_encode(const double *samples, uint64_t n, uint8_t *out, uint6
 int64_t atsc_csv_read_values(const char *text, uint64_t len, int has_header, const char *time_field,
                              const char *value_field, double *out, uint64_t cap);
 
+/* VSRI timestamp index (vsri/src/lib.rs): per series a list of line segments
+ * [sample rate, first sample, first timestamp, samples]; text image "min\nmax\nm,x0,y0,n\n...".
+ * The csv-compressor CLI stores it beside the .bro file (csv-compressor/src/main.rs:141-211).
+ * Getters return 1 and the value, or 0 where the reference returns None. */
+typedef struct atsc_vsri atsc_vsri;
+atsc_vsri *atsc_vsri_new(void);
+void atsc_vsri_free(atsc_vsri *v);
+int32_t atsc_day_elapsed_seconds(int64_t timestamp_sec);           /* lib.rs:31-40 */
+int atsc_vsri_update_for_point(atsc_vsri *v, int32_t y);           /* lib.rs:249-285; 1 = point in the past */
+int32_t atsc_vsri_min(const atsc_vsri *v);
+int32_t atsc_vsri_max(const atsc_vsri *v);
+int32_t atsc_vsri_sample_count(const atsc_vsri *v);                /* lib.rs:368-371 */
+uint64_t atsc_vsri_segment_count(const atsc_vsri *v);
+int atsc_vsri_get_sample(const atsc_vsri *v, int32_t y, int32_t *x);          /* lib.rs:312-328 */
+int atsc_vsri_get_time(const atsc_vsri *v, int32_t x, int32_t *y);            /* lib.rs:331-353 */
+int atsc_vsri_get_next_sample(const atsc_vsri *v, int32_t y, int32_t *x);     /* lib.rs:156-172 */
+int atsc_vsri_get_previous_sample(const atsc_vsri *v, int32_t y, int32_t *x); /* lib.rs:178-197 */
+int atsc_vsri_is_empty(const atsc_vsri *v, int32_t t0, int32_t t1);           /* lib.rs:202-245 */
+uint64_t atsc_vsri_all_timestamps(const atsc_vsri *v, int32_t *out, uint64_t cap); /* lib.rs:356-366 */
+uint64_t atsc_vsri_to_text(const atsc_vsri *v, char *out, uint64_t cap);      /* lib.rs:442-462 */
+atsc_vsri *atsc_vsri_from_text(const char *text, uint64_t len);               /* lib.rs:466-497; NULL = malformed */
+
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t atsc_gpu_launch_count(const atsc_ctx *ctx);
 
