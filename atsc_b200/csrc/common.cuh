@@ -193,12 +193,13 @@ __device__ inline double round_f64_dec(double x, int decimals) {
     return __ddiv_rn(round(__dmul_rn(x, y)), y);
 }
 
-// f64::round (half away from zero) without the library call: trunc + exact remainder test
+// f64::round (half away from zero) without the library call: trunc(y + copysign(pred(0.5), y)).
+// Exact for every double: a fraction below one half stays below the next integer after the
+// addition (the sum is at least 2^-54 short of it, which survives rounding at any exponent where
+// fractions exist), a fraction of one half or more reaches it, and from 2^52 on y is an integer
+// that the addend cannot move.  NaN, +-inf and -0.0 pass through like f64::round.
 __device__ __forceinline__ double round_half_away(double y) {
-    double r = trunc(y);
-    double diff = __dsub_rn(y, r);  // exact
-    if (fabs(diff) >= 0.5) r = __dadd_rn(r, copysign(1.0, y));
-    return r;
+    return trunc(__dadd_rn(y, copysign(0.49999999999999994, y)));
 }
 // n / 100000.0, correctly rounded, for the integer-valued n that `round()` returns: Markstein's
 // two-step FMA refinement of n * RN(1/100000) (q1 is already faithful, q2 is the IEEE quotient;
@@ -211,6 +212,18 @@ __device__ __forceinline__ double div_1e5(double n) {
     q = __fma_rn(__fma_rn(-b, q, n), y, q);
     return fabs(n) == __longlong_as_double(0x7FF0000000000000ll) ? n : q;
 }
+// The same quotient for an INTEGER n with |n| < 2^53 in one refinement step.  q0 = RN(n*y) is within
+// 1.24 ulp of n/1e5 (y = RN(1e-5) is 2^-53.44 relative above 1e-5), so r = n - 1e5*q0 is a multiple
+// of 32 ulp(q0) below 2^12 of them: exact.  q0 + r/1e5 IS n/1e5, r*y differs from r/1e5 by < 1e-16
+// ulp, and n/1e5 is either a double or at least 5e-6 ulp away from every midpoint between doubles
+// (it cannot be a midpoint: 3125 | n would make it a 42-bit dyadic), so the last rounding lands on
+// RN(n/1e5).  No inf pass-through: callers guarantee finite n (tools/div_check.py replays the proof
+// in exact rational arithmetic).
+__device__ __forceinline__ double div_1e5_int53(double n) {
+    const double b = 100000.0, y = 1e-5;
+    const double q = __dmul_rn(n, y);
+    return __fma_rn(__fma_rn(-b, q, n), y, q);
+}
 // 1 / o to ~2^-45 relative, branch free: hardware seed (2^-23) + one Newton step.  The error loops
 // only need the MAPE terms far inside the near-tie margins (1e-10 absolute on the mean, see
 // mape_term).  o == 0 or denormal -> the seed itself (+-inf), like the IEEE quotient of a zero
@@ -222,12 +235,21 @@ __device__ __forceinline__ double rcp_fast(double o) {
     const double y1 = __fma_rn(y, __fma_rn(-o, y, 1.0), y);
     return y1 == y1 ? y1 : y;
 }
+// rcp_fast for a normal, finite, nonzero o well inside the exponent range: no NaN select needed
+__device__ __forceinline__ double rcp_fast_tame(double o) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(o));
+    return __fma_rn(y, __fma_rn(-o, y, 1.0), y);
+}
 // One MAPE term |(out - o) / o| (utils/error.rs:110-113) through a reciprocal good to ~3e-14
 // relative (absorbed by the near-tie tolerance, the error only feeds threshold tests); an exactly
 // reproduced sample gives exactly 0.  A zero sample keeps the reference's
 // semantics: w = inf gives inf (out != 0) or NaN (out == 0), SURVEY H5.
 __device__ __forceinline__ double mape_term(double out, double o) {
     return fabs(__dmul_rn(__dsub_rn(out, o), rcp_fast(o)));
+}
+__device__ __forceinline__ double mape_term_tame(double out, double o) {
+    return fabs(__dmul_rn(__dsub_rn(out, o), rcp_fast_tame(o)));
 }
 
 // optimizer/utils.rs:115-160 split_n: (integer part as i64, fraction != 0)
