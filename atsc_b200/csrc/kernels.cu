@@ -40,8 +40,7 @@ __device__ inline FftWs fft_slot(const SlotPool &p, int s) {
 // =========================================================================================
 // stats
 // =========================================================================================
-template <int VAR>
-__global__ void __launch_bounds__(256, VAR == 2 ? 4 : 8) k_stats(const FrameWork *__restrict__ fr, const ChunkRef *__restrict__ chunks,
+__global__ void __launch_bounds__(256, 8) k_stats(const FrameWork *__restrict__ fr, const ChunkRef *__restrict__ chunks,
                                                     uint32_t n_chunks, const double *__restrict__ samples,
                                                     StatsPart *parts, unsigned *q) {
     __shared__ StatsSmem sm;
@@ -51,10 +50,7 @@ __global__ void __launch_bounds__(256, VAR == 2 ? 4 : 8) k_stats(const FrameWork
         if (c >= (int)n_chunks) break;
         const ChunkRef ch = chunks[c];
         const FrameWork *fw = &fr[ch.frame];
-        if (VAR == 0)
-            chunk_stats(samples + fw->off, fw->len, ch.start, min(ch.start + STATS_CHUNK, fw->len), parts + c, &sm);
-        else
-            chunk_stats2<VAR == 2 ? 4 : 2>(samples + fw->off, fw->len, ch.start, min(ch.start + STATS_CHUNK, fw->len), parts + c, &sm);
+        chunk_stats(samples + fw->off, fw->len, ch.start, min(ch.start + STATS_CHUNK, fw->len), parts + c, &sm);
     }
 }
 
@@ -103,7 +99,6 @@ __global__ void k_plan(FrameWork *fr, uint32_t n, const double *__restrict__ sam
 // =========================================================================================
 // polynomial / idw
 // =========================================================================================
-template <int VAR>
 __global__ void __launch_bounds__(512, 2) k_poly(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
                                                 double max_err, const double *__restrict__ inv_d2, SlotPool pool,
                                                 unsigned *q) {
@@ -116,7 +111,7 @@ __global__ void __launch_bounds__(512, 2) k_poly(FrameWork *fr, uint32_t n, cons
         if (i >= (int)n) break;
         FrameWork *fw = &fr[i];
         if (!fw->need_poly) continue;
-        poly_frame<VAR>(samples + fw->off, fw, max_err, inv_d2, shd, ws);
+        poly_frame(samples + fw->off, fw, max_err, inv_d2, shd, ws);
     }
 }
 
@@ -1132,37 +1127,14 @@ static inline int grid_for(uint32_t n, int slots) { return (int)(n < (uint32_t)s
 
 void launch_stats(const FrameWork *fr, const ChunkRef *chunks, uint32_t n_chunks, const double *samples, StatsPart *parts,
                   unsigned *q, cudaStream_t st) {
-    const int var = getenv("ATSC_STATS_VARIANT") ? atoi(getenv("ATSC_STATS_VARIANT")) : 1;
-    if (var == 1)
-        k_stats<1><<<grid_for(n_chunks, 8 * sms()), 256, 0, st>>>(fr, chunks, n_chunks, samples, parts, q);
-    else if (var == 2)
-        k_stats<2><<<grid_for(n_chunks, 4 * sms()), 256, 0, st>>>(fr, chunks, n_chunks, samples, parts, q);
-    else
-        k_stats<0><<<grid_for(n_chunks, 8 * sms()), 256, 0, st>>>(fr, chunks, n_chunks, samples, parts, q);
+    k_stats<<<grid_for(n_chunks, 8 * sms()), 256, 0, st>>>(fr, chunks, n_chunks, samples, parts, q);
 }
 void launch_plan(FrameWork *fr, uint32_t n, const double *samples, const StatsPart *parts, cudaStream_t st) {
     k_plan<<<(n + 63) / 64, 64, 0, st>>>(fr, n, samples, parts);
 }
 void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_err, const double *inv_d2,
                  SlotPool pool, unsigned *q, cudaStream_t st) {
-    const int var = getenv("ATSC_POLY_VARIANT") ? atoi(getenv("ATSC_POLY_VARIANT")) : 3;
-    if (var == 1)
-        k_poly<1><<<grid_for(n, pool.poly_slots), 512, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);
-    else if (var == 2)
-        k_poly<2><<<grid_for(n, pool.poly_slots), 512, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);
-    else if (var == 3)
-        k_poly<3><<<grid_for(n, pool.poly_slots), 512, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);
-    else if (var == 4)
-        k_poly<4><<<grid_for(n, pool.poly_slots), 512, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);
-    else if (var == 5)
-        k_poly<5><<<grid_for(n, pool.poly_slots), 512, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);
-    else if (var == 6)
-        k_poly<6><<<grid_for(n, pool.poly_slots), 512, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);
-    else if (var == 7)
-        k_poly<7><<<grid_for(n, pool.poly_slots), 512, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);
-
-    else
-        k_poly<0><<<grid_for(n, pool.poly_slots), 512, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);
+    k_poly<<<grid_for(n, pool.poly_slots), 512, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);
 }
 void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err, SlotPool pool, unsigned *q,
                 cudaStream_t st) {

@@ -137,7 +137,7 @@ __device__ __forceinline__ bool poly_tame(double vmin, double vmax) {
 // walks over segments, so the inner loop has no table lookups, no index division and no branches;
 // the per-key tangents come from a pre-pass.
 // TAME selects the guard-free arithmetic of a tame frame (same values, fewer instructions).
-template <bool TAME, int VAR>
+template <bool TAME>
 __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys &k, int ptype,
                                    double vmin, double vmax, const double *__restrict__ inv_d2,
                                    PolyWs ws, double *scratch) {
@@ -184,121 +184,33 @@ __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys 
             const uint32_t xa = i * step;
             return term(hermite(d[xa], tang[i], d[xa + step], tang[i + 1]), d[xa + j]);
         };
-        if (VAR == 0) {
-            // two segments per trip: their (long, strictly serial) f64 chains are independent, and with
-            // every helper branch free the compiler interleaves them
-            uint32_t i = 1 + g;
-            for (; i + G <= i_hi; i += 2 * G) {  // both segments of the trip exist
-                const double e1 = seg_err(i), e2 = seg_err(i + G);
-                acc += e1;
-                acc += e2;
+        // NS adjacent segments per trip through running pointers: the NS - 1 inner keys and tangents are
+        // loaded once for the two segments they belong to, and 3 * NS + 2 loads are in flight per thread.
+        // The loop waits on memory, not on issue slots: with the same arithmetic, two segments per trip
+        // took 1.00 ms per bench step, two with one-trip-ahead register prefetch 0.89, four 0.78 (B200).
+        constexpr int NS = 4;
+        const uint32_t nblk = i_hi / NS;  // segments 1 .. i_hi in blocks of NS
+        const double *p = d + (size_t)(1 + NS * g) * step, *tg = tang + 1 + NS * g;
+        const double *po = p + j;  // this thread's samples
+        const size_t stride = (size_t)NS * G * step;
+        for (uint32_t q = g; q < nblk; q += G) {
+            double kv[NS + 1], tv[NS + 1], o[NS], e[NS];
+#pragma unroll
+            for (int u = 0; u <= NS; u++) {
+                kv[u] = p[(uint32_t)u * step];
+                tv[u] = tg[u];
             }
-            if (i <= i_hi) acc += seg_err(i);
-        } else if (VAR == 1) {
-            // two ADJACENT segments per trip: the middle key and its tangent are loaded once for both
-            uint32_t i = 1 + 2 * g;
-            for (; i + 1 <= i_hi; i += 2 * G) {
-                const uint32_t xa = i * step;
-                const double bv = d[xa + step], tb = tang[i + 1];
-                const double v1 = hermite(d[xa], tang[i], bv, tb), v2 = hermite(bv, tb, d[xa + 2 * step], tang[i + 2]);
-                const double e1 = term(v1, d[xa + j]), e2 = term(v2, d[xa + step + j]);
-                acc += e1;
-                acc += e2;
-            }
-            if (i <= i_hi) acc += seg_err(i);
-        } else if (VAR == 7) {
-            // four adjacent segments per trip, addresses from the segment index
-            constexpr int NS = 4;
-            const uint32_t nblk = i_hi / NS;
-            for (uint32_t q = g; q < nblk; q += G) {
-                const uint32_t i = 1 + NS * q, xa = i * step;
-                double kv[NS + 1], tv[NS + 1], o[NS], e[NS];
 #pragma unroll
-                for (int u = 0; u <= NS; u++) {
-                    kv[u] = d[xa + (uint32_t)u * step];
-                    tv[u] = tang[i + u];
-                }
+            for (int u = 0; u < NS; u++) o[u] = po[(uint32_t)u * step];
 #pragma unroll
-                for (int u = 0; u < NS; u++) o[u] = d[xa + (uint32_t)u * step + j];
+            for (int u = 0; u < NS; u++) e[u] = term(hermite(kv[u], tv[u], kv[u + 1], tv[u + 1]), o[u]);
 #pragma unroll
-                for (int u = 0; u < NS; u++) e[u] = term(hermite(kv[u], tv[u], kv[u + 1], tv[u + 1]), o[u]);
-#pragma unroll
-                for (int u = 0; u < NS; u++) acc += e[u];
-            }
-            for (uint32_t i = nblk * NS + 1 + g; i <= i_hi; i += G) acc += seg_err(i);
-        } else {
-            // NS adjacent segments per trip through running pointers: the NS - 1 inner keys and tangents
-            // are loaded once for the two segments they belong to, there is no per-trip index -> address
-            // arithmetic, and 3 * NS + 2 loads are in flight per thread
-            constexpr int NS = VAR == 3 ? 4 : 2;
-            const uint32_t nblk = i_hi / NS;  // segments 1 .. i_hi in blocks of NS
-            const double *p = d + (size_t)(1 + NS * g) * step, *tg = tang + 1 + NS * g;
-            const size_t stride = (size_t)NS * G * step;
-            const double *po = p + j;  // this thread's samples
-            if (VAR >= 5) {
-                // the samples are the loads that come from DRAM (keys and tangents were touched by the
-                // pre-pass: L2): they are fetched one trip ahead into registers
-                double o[NS], kv[NS + 1];
-                if (g < nblk) {
-#pragma unroll
-                    for (int u = 0; u < NS; u++) o[u] = po[(uint32_t)u * step];
-                    if (VAR == 6) {
-#pragma unroll
-                        for (int u = 0; u <= NS; u++) kv[u] = p[(uint32_t)u * step];
-                    }
-                }
-                for (uint32_t q = g; q < nblk; q += G) {
-                    double tv[NS + 1], no[NS], nkv[NS + 1], e[NS];
-                    if (VAR == 5) {
-#pragma unroll
-                        for (int u = 0; u <= NS; u++) kv[u] = p[(uint32_t)u * step];
-                    }
-#pragma unroll
-                    for (int u = 0; u <= NS; u++) tv[u] = tg[u];
-                    p += stride;
-                    po += stride;
-                    tg += NS * G;
-                    if (q + G < nblk) {
-#pragma unroll
-                        for (int u = 0; u < NS; u++) no[u] = po[(uint32_t)u * step];
-                        if (VAR == 6) {
-#pragma unroll
-                            for (int u = 0; u <= NS; u++) nkv[u] = p[(uint32_t)u * step];
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < NS; u++) e[u] = term(hermite(kv[u], tv[u], kv[u + 1], tv[u + 1]), o[u]);
-#pragma unroll
-                    for (int u = 0; u < NS; u++) acc += e[u];
-#pragma unroll
-                    for (int u = 0; u < NS; u++) o[u] = no[u];
-                    if (VAR == 6) {
-#pragma unroll
-                        for (int u = 0; u <= NS; u++) kv[u] = nkv[u];
-                    }
-                }
-            } else
-            for (uint32_t q = g; q < nblk; q += G) {
-                double kv[NS + 1], tv[NS + 1], o[NS], e[NS];
-                if (VAR == 4 && q + 4 * G < nblk)  // pull the samples of four trips ahead into L2
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(po + 4 * stride));
-#pragma unroll
-                for (int u = 0; u <= NS; u++) {
-                    kv[u] = p[(uint32_t)u * step];
-                    tv[u] = tg[u];
-                }
-#pragma unroll
-                for (int u = 0; u < NS; u++) o[u] = po[(uint32_t)u * step];
-#pragma unroll
-                for (int u = 0; u < NS; u++) e[u] = term(hermite(kv[u], tv[u], kv[u + 1], tv[u + 1]), o[u]);
-#pragma unroll
-                for (int u = 0; u < NS; u++) acc += e[u];
-                p += stride;
-                po += stride;
-                tg += NS * G;
-            }
-            for (uint32_t i = nblk * NS + 1 + g; i <= i_hi; i += G) acc += seg_err(i);  // fewer than NS left over
+            for (int u = 0; u < NS; u++) acc += e[u];
+            p += stride;
+            po += stride;
+            tg += NS * G;
         }
+        for (uint32_t i = nblk * NS + 1 + g; i <= i_hi; i += G) acc += seg_err(i);  // fewer than NS left over
     }
     // ---- the Linear ends: segment 0, segment K-2 (possibly irregular) and the last sample
     const uint32_t Kreg = k.Kreg;
@@ -421,7 +333,6 @@ __device__ inline bool poly_loop_near_tie(double cur, double target) {
 
 // Runs the reference's refinement loop for one frame. All threads of the CTA call.
 // Writes poly_* fields of fw (thread 0).  `sh` = shared scratch (>= 40 doubles).
-template <int VAR>
 __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, double max_err,
                                   const double *__restrict__ inv_d2, double *sh, PolyWs ws) {
     const uint32_t N = fw->len;
@@ -457,8 +368,8 @@ __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, d
                 } else if (step == 1 && it <= 22) {
                     cur = 0.0;  // value unused: the `len == data_len` exit below overrides it
                 } else {
-                    cur = tame ? poly_mape<true, VAR>(d, k, ptype, vmin, vmax, inv_d2, ws, sh)
-                               : poly_mape<false, VAR>(d, k, ptype, vmin, vmax, inv_d2, ws, sh);
+                    cur = tame ? poly_mape<true>(d, k, ptype, vmin, vmax, inv_d2, ws, sh)
+                               : poly_mape<false>(d, k, ptype, vmin, vmax, inv_d2, ws, sh);
                 }
                 prev_step = step;
                 prev_err = cur;

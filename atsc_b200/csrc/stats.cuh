@@ -31,46 +31,6 @@ __device__ inline bool frac_nonzero(double x) {
     return f;
 }
 
-// per-sample accumulators of one thread
-struct StatsAcc {
-    double mn, mx;
-    uint32_t flags;  // bit0 fractional, bit1 saw -0.0, bit2 saw 0 < |x| < 2^-64 (fractional needs the exact test)
-    uint32_t ends, ends251, ends64k;  // run ends before the last sample: all / at i+1 >= 251 / at i+1 >= 65536
-};
-
-// sample with value val, right-hand neighbour nx and index i1 - 1.
-// UNIFORM: every index of the chunk is on the same side of the varint thresholds (the caller
-// scales `ends`); RUNS = false: value part only.
-template <bool UNIFORM, bool RUNS = true>
-__device__ __forceinline__ void stats_sample(StatsAcc &a, double val, double nx, uint32_t i1) {
-    const int hi = __double2hiint(val);
-    if (!(a.flags & 1u)) {
-        // fractional (split_n): r = (x + copysign(2^52, x)) - copysign(2^52, x) is x rounded to an integer
-        // for |x| < 2^52 and x itself beyond (integers, inf), so "r <> x" (ordered: NaN is not
-        // fractional) is exactly "x has a fractional part"; the sliver 0 < |x| < 2^-64, which split_n
-        // does not call fractional, is settled by finish_stats
-        const double magic = __hiloint2double((hi & (int)0x80000000) | 0x43300000, 0);
-        const double r = __dsub_rn(__dadd_rn(val, magic), magic);
-        if (r < val || r > val) {
-            const uint32_t ef = (uint32_t)hi & 0x7FF00000u;
-            a.flags |= ef >= 0x3BF00000u ? 1u : 4u;
-        }
-    }
-    if (hi == (int)0x80000000 && __double2loint(val) == 0) a.flags |= 2u;
-    // strict comparisons: NaN never wins (optimizer/utils.rs:57-64); the sign of a zero extreme is
-    // settled afterwards (finish_stats)
-    if (val < a.mn) a.mn = val;
-    if (val > a.mx) a.mx = val;
-    // rle.rs:154: a run ends where the next value differs
-    if (RUNS && nx != val) {
-        a.ends++;
-        if (!UNIFORM) {
-            a.ends251 += (i1 >= 251u) ? 1u : 0u;
-            a.ends64k += (i1 >= 65536u) ? 1u : 0u;
-        }
-    }
-}
-
 // One work item of k_stats: samples [start, start + STATS_CHUNK) of a frame.  Frames are cut into
 // chunks so the pass balances over the SMs no matter how few frames a wave has.
 constexpr uint32_t STATS_CHUNK = 32768;
@@ -82,96 +42,48 @@ struct StatsPart {
     uint32_t flags, ends, ends251, ends64k;
 };
 
-template <bool UNIFORM>
-__device__ __forceinline__ void chunk_scan(StatsAcc &a, const double *__restrict__ dc, uint32_t n, uint32_t c0) {
-    const uint32_t T = blockDim.x, t = threadIdx.x;
-    const int ln = t & 31;
-    const bool vec = (((uintptr_t)dc >> 3) & 1u) == 0u;  // 16-byte aligned chunk: two samples per load
-    if (vec) {
-        constexpr uint32_t U = 2;
-        const double2 *d2 = reinterpret_cast<const double2 *>(dc);
-        const uint32_t P = n / 2;  // pairs whose second element still has a neighbour
-        const uint32_t Pfull = P - P % (U * T);
-        uint32_t p0 = 0;
-        for (; p0 < Pfull; p0 += U * T) {  // every pair of the tile exists and has a successor pair or dc[2P]
-            double2 v[U];
-#pragma unroll
-            for (uint32_t u = 0; u < U; u++) v[u] = __ldcs(d2 + p0 + u * T + t);  // streamed once: do not keep in L1 / L2
-#pragma unroll
-            for (uint32_t u = 0; u < U; u++) {
-                const uint32_t p = p0 + u * T + t;
-                double nx = __shfl_down_sync(0xffffffffu, v[u].x, 1);
-                if (ln == 31) nx = dc[2 * p + 2];
-                stats_sample<UNIFORM>(a, v[u].x, v[u].y, c0 + 2 * p + 1);
-                stats_sample<UNIFORM>(a, v[u].y, nx, c0 + 2 * p + 2);
-            }
-        }
-        for (; p0 < P; p0 += T) {
-            const uint32_t p = p0 + t;
-            const double2 v = p < P ? __ldg(d2 + p) : make_double2(0.0, 0.0);
-            double nx = __shfl_down_sync(0xffffffffu, v.x, 1);
-            if ((ln == 31 || p + 1 >= P) && p < P) nx = dc[2 * p + 2];
-            if (p < P) {
-                stats_sample<UNIFORM>(a, v.x, v.y, c0 + 2 * p + 1);
-                stats_sample<UNIFORM>(a, v.y, nx, c0 + 2 * p + 2);
-            }
-        }
-        for (uint32_t i = 2 * P + t; i < n; i += T) stats_sample<UNIFORM>(a, dc[i], dc[i + 1], c0 + i + 1);  // <= 1 leftover
-    } else {
-        constexpr uint32_t U = 4;
-        for (uint32_t i0 = 0; i0 < n; i0 += U * T) {
-            double v[U];
-#pragma unroll
-            for (uint32_t u = 0; u < U; u++) v[u] = (i0 + u * T + t < n) ? dc[i0 + u * T + t] : 0.0;
-#pragma unroll
-            for (uint32_t u = 0; u < U; u++) {
-                const uint32_t i = i0 + u * T + t;
-                double nx = __shfl_down_sync(0xffffffffu, v[u], 1);
-                if ((ln == 31 || i + 1 >= n) && i < n) nx = dc[i + 1];
-                if (i < n) stats_sample<UNIFORM>(a, v[u], nx, c0 + i + 1);
-            }
-        }
-    }
-}
-
-// ---- second formulation of the scan (same partials).  Per sample it issues about half the
-// instructions of chunk_scan: the right-hand neighbour comes from a plain 8-byte load at the vector
-// load's address + 16 (no shuffle, no lane-31 fix-up), the fractional test is gated once per trip,
-// the -0.0 test is a running unsigned minimum, and the run-end index classes never need per-sample
+// The scan keeps the per-sample instruction count low (the pass is issue bound well before it is
+// HBM bound): the right-hand neighbour comes from a plain 8-byte load at the vector load's
+// address + 16 (no shuffle, no lane-31 fix-up), the fractional test is gated once per trip, the
+// -0.0 test is a running unsigned minimum, and the run-end index classes need no per-sample
 // counters because the caller scans each index class [0,250) [250,65535) [65535,..) on its own.
-struct StatsAcc2 {
+struct StatsAcc {
     double mn, mx;
     uint32_t flags;  // bit0 fractional, bit2 saw 0 < |x| < 2^-64
     uint32_t negz;   // min over samples of lo | (hi ^ 0x80000000): 0 <=> a -0.0 was seen
     uint32_t ends;   // run ends
 };
-__device__ __forceinline__ void stats_frac2(StatsAcc2 &a, double val) {
+__device__ __forceinline__ void stats_frac(StatsAcc &a, double val) {
     const int hi = __double2hiint(val);
     const double magic = __hiloint2double((hi & (int)0x80000000) | 0x43300000, 0);
-    const double r = __dsub_rn(__dadd_rn(val, magic), magic);  // see stats_sample
+    // fractional (split_n): r = (x + copysign(2^52, x)) - copysign(2^52, x) is x rounded to an integer
+    // for |x| < 2^52 and x itself beyond (integers, inf), so "r <> x" (ordered: NaN is not
+    // fractional) is exactly "x has a fractional part"; the sliver 0 < |x| < 2^-64, which split_n
+    // does not call fractional, is settled by finish_stats
+    const double r = __dsub_rn(__dadd_rn(val, magic), magic);
     if (r < val || r > val) a.flags |= ((uint32_t)hi & 0x7FF00000u) >= 0x3BF00000u ? 1u : 4u;
 }
-__device__ __forceinline__ void stats_value2(StatsAcc2 &a, double val) {
+__device__ __forceinline__ void stats_value(StatsAcc &a, double val) {
     a.negz = min(a.negz, (uint32_t)__double2loint(val) | ((uint32_t)__double2hiint(val) ^ 0x80000000u));
     if (val < a.mn) a.mn = val;  // strict: NaN never wins (optimizer/utils.rs:57-64)
     if (val > a.mx) a.mx = val;
 }
 // samples dc[0 .. n): every one has a right-hand neighbour dc[i + 1] inside the frame
-template <uint32_t U>
-__device__ __forceinline__ void chunk_scan2(StatsAcc2 &a, const double *__restrict__ dc, uint32_t n) {
+__device__ __forceinline__ void chunk_scan(StatsAcc &a, const double *__restrict__ dc, uint32_t n) {
     const uint32_t T = blockDim.x, t = threadIdx.x;
     uint32_t done = 0;
     if (n && (((uintptr_t)dc >> 3) & 1u)) {  // odd start: one scalar sample, then 16-byte aligned
         if (t == 0) {
             const double v = dc[0];
-            if (!(a.flags & 1u)) stats_frac2(a, v);
-            stats_value2(a, v);
+            if (!(a.flags & 1u)) stats_frac(a, v);
+            stats_value(a, v);
             a.ends += (dc[1] != v) ? 1u : 0u;
         }
         done = 1;
     }
     const double2 *d2 = reinterpret_cast<const double2 *>(dc + done);
     const uint32_t P = (n - done) / 2;
+    constexpr uint32_t U = 2;  // vector loads in flight per thread (four were no faster, at half the occupancy)
     const uint32_t Pfull = P - P % (U * T);
     uint32_t p0 = 0;
     for (; p0 < Pfull; p0 += U * T) {
@@ -186,14 +98,14 @@ __device__ __forceinline__ void chunk_scan2(StatsAcc2 &a, const double *__restri
         if (!(a.flags & 1u)) {
 #pragma unroll
             for (uint32_t u = 0; u < U; u++) {
-                stats_frac2(a, v[u].x);
-                stats_frac2(a, v[u].y);
+                stats_frac(a, v[u].x);
+                stats_frac(a, v[u].y);
             }
         }
 #pragma unroll
         for (uint32_t u = 0; u < U; u++) {
-            stats_value2(a, v[u].x);
-            stats_value2(a, v[u].y);
+            stats_value(a, v[u].x);
+            stats_value(a, v[u].y);
             a.ends += (v[u].y != v[u].x) ? 1u : 0u;
             a.ends += (nx[u] != v[u].y) ? 1u : 0u;
         }
@@ -203,27 +115,26 @@ __device__ __forceinline__ void chunk_scan2(StatsAcc2 &a, const double *__restri
         const double2 v = __ldcs(q);
         const double nx = __ldg(reinterpret_cast<const double *>(q + 1));
         if (!(a.flags & 1u)) {
-            stats_frac2(a, v.x);
-            stats_frac2(a, v.y);
+            stats_frac(a, v.x);
+            stats_frac(a, v.y);
         }
-        stats_value2(a, v.x);
-        stats_value2(a, v.y);
+        stats_value(a, v.x);
+        stats_value(a, v.y);
         a.ends += (v.y != v.x) ? 1u : 0u;
         a.ends += (nx != v.y) ? 1u : 0u;
     }
     if (t == 0 && done + 2 * P < n) {  // one leftover sample
         const double v = dc[n - 1];
-        if (!(a.flags & 1u)) stats_frac2(a, v);
-        stats_value2(a, v);
+        if (!(a.flags & 1u)) stats_frac(a, v);
+        stats_value(a, v);
         a.ends += (dc[n] != v) ? 1u : 0u;
     }
 }
 
-// chunk_stats through chunk_scan2
-template <uint32_t U>
-__device__ inline void chunk_stats2(const double *__restrict__ d, uint32_t N, uint32_t c0, uint32_t c1, StatsPart *out,
+// Partial stats of samples [c0, c1) of a frame of N samples (all threads call; thread 0 writes *out).
+__device__ inline void chunk_stats(const double *__restrict__ d, uint32_t N, uint32_t c0, uint32_t c1, StatsPart *out,
                                     StatsSmem *sm) {
-    StatsAcc2 a;
+    StatsAcc a;
     a.mn = __longlong_as_double(0x7FF0000000000000ll);
     a.mx = -a.mn;
     a.flags = 0;
@@ -238,81 +149,17 @@ __device__ inline void chunk_stats2(const double *__restrict__ d, uint32_t N, ui
         const uint32_t lo = max(c0, k == 0 ? 0u : k == 1 ? 250u : 65535u), hi = min(e, k == 0 ? 250u : k == 1 ? 65535u : 0xFFFFFFFFu);
         if (lo >= hi) continue;
         a.ends = 0;
-        chunk_scan2<U>(a, d + lo, hi - lo);
+        chunk_scan(a, d + lo, hi - lo);
         idx3[0] += a.ends;
         if (k >= 1) idx3[1] += a.ends;
         if (k >= 2) idx3[2] += a.ends;
     }
     if (t == 0 && c1 == N) {  // the frame's last sample
         const double v = d[N - 1];
-        if (!(a.flags & 1u)) stats_frac2(a, v);
-        stats_value2(a, v);
+        if (!(a.flags & 1u)) stats_frac(a, v);
+        stats_value(a, v);
     }
     if (a.negz == 0u) a.flags |= 2u;
-    const int lane = t & 31, w = t >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a.mn = fmin(a.mn, __shfl_down_sync(0xffffffffu, a.mn, o));
-        a.mx = fmax(a.mx, __shfl_down_sync(0xffffffffu, a.mx, o));
-        a.flags |= __shfl_down_sync(0xffffffffu, a.flags, o);
-#pragma unroll
-        for (int k = 0; k < 3; k++) idx3[k] += __shfl_down_sync(0xffffffffu, idx3[k], o);
-    }
-    __syncthreads();
-    if (lane == 0) {
-        sm->mn[w] = a.mn;
-        sm->mx[w] = a.mx;
-        sm->flags[w] = a.flags;
-        sm->runs[w] = idx3[0];
-        sm->idxb[w] = idx3[1];
-        sm->e64k[w] = idx3[2];
-    }
-    __syncthreads();
-    if (w == 0) {
-        const int nw = T >> 5;
-        double mn = lane < nw ? sm->mn[lane] : a.mn, mx = lane < nw ? sm->mx[lane] : a.mx;
-        uint32_t fl = lane < nw ? sm->flags[lane] : 0u;
-        uint32_t r0 = lane < nw ? sm->runs[lane] : 0u, r1 = lane < nw ? sm->idxb[lane] : 0u, r2 = lane < nw ? sm->e64k[lane] : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, o));
-            mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
-            fl |= __shfl_down_sync(0xffffffffu, fl, o);
-            r0 += __shfl_down_sync(0xffffffffu, r0, o);
-            r1 += __shfl_down_sync(0xffffffffu, r1, o);
-            r2 += __shfl_down_sync(0xffffffffu, r2, o);
-        }
-        if (lane == 0) {
-            StatsPart p;
-            p.mn = mn;
-            p.mx = mx;
-            p.flags = fl;
-            p.ends = r0;
-            p.ends251 = r1;
-            p.ends64k = r2;
-            *out = p;
-        }
-    }
-}
-
-// Partial stats of samples [c0, c1) of a frame of N samples (all threads call; thread 0 writes *out).
-__device__ inline void chunk_stats(const double *__restrict__ d, uint32_t N, uint32_t c0, uint32_t c1, StatsPart *out,
-                                   StatsSmem *sm) {
-    StatsAcc a;
-    a.mn = __longlong_as_double(0x7FF0000000000000ll);
-    a.mx = -a.mn;
-    a.flags = a.ends = a.ends251 = a.ends64k = 0;
-    const uint32_t T = blockDim.x, t = threadIdx.x;
-    // samples [c0, e) have a right-hand neighbour inside the frame; a frame's last sample is value-only
-    const uint32_t e = min(c1, N - 1);
-    // varint_len(i + 1) of the run ends is the same for the whole chunk unless it straddles 251 / 65536
-    const bool hi = c0 + 1 >= 65536u, mid = c0 + 1 >= 251u && e < 65536u, lo = e < 251u;
-    if (hi || mid || lo)
-        chunk_scan<true>(a, d + c0, e - c0, c0);
-    else
-        chunk_scan<false>(a, d + c0, e - c0, c0);
-    if (t == 0 && c1 == N) stats_sample<true, false>(a, d[N - 1], 0.0, 0);  // the frame's last sample
-    uint32_t idx3[3] = {a.ends, (hi || mid) ? a.ends : a.ends251, hi ? a.ends : a.ends64k};
     const int lane = t & 31, w = t >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
