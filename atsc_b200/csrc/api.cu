@@ -164,23 +164,23 @@ void radices_of(uint32_t len, FftStage *stg, uint32_t *ns) {
     // radices {9, 8, 4, 3, 2}: as few Stockham stages (shared-memory round trips) as possible
     uint8_t rad[16];
     uint32_t k = 0, n = len;
-    while (n % 9 == 0) {
+    while (n % 9 == 0 && k < sizeof rad) {
         rad[k++] = 9;
         n /= 9;
     }
-    while (n % 8 == 0) {
+    while (n % 8 == 0 && k < sizeof rad) {
         rad[k++] = 8;
         n /= 8;
     }
-    while (n % 4 == 0) {
+    while (n % 4 == 0 && k < sizeof rad) {
         rad[k++] = 4;
         n /= 4;
     }
-    while (n % 2 == 0) {
+    while (n % 2 == 0 && k < sizeof rad) {
         rad[k++] = 2;
         n /= 2;
     }
-    while (n % 3 == 0) {
+    while (n % 3 == 0 && k < sizeof rad) {
         rad[k++] = 3;
         n /= 3;
     }
