@@ -382,8 +382,9 @@ def main():
                 "note": "achieved / frac / kernel_ms_per_step: CUDA events on each engine's stream inside the timed region "
                         "(waves of several engines overlap, so these durations include contention and add up to more "
                         "than the step); one_engine: the same kernels with a single engine, i.e. each launch alone on "
-                        "the GPU, which is the figure to hold against the kernel's own roofline; k_poly is FP64-latency bound, k_fft_fwd FP32/shared-memory bound, k_stats issue "
-                        "bound (DESIGN.md section 4); the HBM line is the task's stated denominator"}
+                        "the GPU, which is the figure to hold against the kernel's own roofline; k_poly and k_fft_fwd wait on "
+                        "loads (ncu long-scoreboard stalls), k_stats runs near the HBM line (DESIGN.md section 4); the HBM "
+                        "line is the task's stated denominator"}
 
     # ---- decompression of the fleet just produced (device-resident output)
     frames_in, po = [], 0
