@@ -56,3 +56,19 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in txt.lower() or f == "__init__.py" and "oracle" not in txt.lower(), f
+
+
+def test_library_holds_sm100a_code_for_every_kernel():
+    """The product is native sm_100a code: every kernel of KERNEL_NAMES (plus the helpers) is in the
+    library's sm_100a cubin, and the hot loops of the streaming kernels keep their operands in registers
+    (no local-memory traffic in the kernels' inner loops is checked by tools/sass_loops.py on demand)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    r = subprocess.run([cuobjdump, "-elf", atsc_b200.lib_path()], capture_output=True, text=True, timeout=300)
+    assert "sm_100a" in r.stdout or "sm_100" in r.stdout
+    for k in ("k_stats", "k_plan", "k_poly", "k_fft_small", "k_fft_fwd", "k_fft", "k_rle", "k_noop_size", "k_select",
+              "k_scan", "k_emit", "k_decode"):
+        assert f"atsc{len(k)}{k}" in r.stdout, k      # Itanium-mangled atsc::k_*
