@@ -188,13 +188,14 @@ extern "C" int atsc_gpu_decompress_series(atsc_ctx *ctx, const uint8_t *bro_buf,
             if (!get_varint(p, len, pos, fsz) || !get_varint(p, len, pos, sc) || !get_varint(p, len, pos, comp) ||
                 !get_varint(p, len, pos, dl))
                 return ATSC_ERR_FORMAT;
-            if (pos + dl > len || comp > 6) return ATSC_ERR_FORMAT;
+            if (dl > len - pos || comp > 6) return ATSC_ERR_FORMAT;  // (pos <= len here; no wrap-around)
             if (comp == ATSC_NOOP) {
                 // noop_to_data ignores sample_count: the stored Vec<i64> decides (noop.rs:79-83)
                 uint64_t q = pos + 1, k;
                 if (dl < 2 || !get_varint(p, pos + dl, q, k)) return ATSC_ERR_FORMAT;
                 sc = k;
             }
+            if (sc > 131072) return ATSC_ERR_FORMAT;  // no writer produces a frame beyond MAX_FRAME_SIZE (optimizer/mod.rs:25)
             if (out_samples && sc) {
                 atsc_frame_in f;
                 memset(&f, 0, sizeof f);
@@ -203,7 +204,6 @@ extern "C" int atsc_gpu_decompress_series(atsc_ctx *ctx, const uint8_t *bro_buf,
                 f.payload_off = bro_off[s] + pos;
                 f.payload_len = (uint32_t)dl;
                 f.out_off = (out_off ? out_off[s] : 0) + total;
-                if (sc > 131072) return ATSC_ERR_FORMAT;
                 frames.push_back(f);
             }
             max_end = std::max(max_end, bro_off[s] + pos + dl);

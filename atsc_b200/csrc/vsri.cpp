@@ -6,6 +6,7 @@
 //   [sample rate m, first sample x0, first timestamp y0, number of samples]
 // written as text:  min_ts \n max_ts \n m,x0,y0,n \n ...
 // Integer semantics are Rust's i32: the divisions truncate toward zero like C++'s.
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -13,6 +14,13 @@
 #include <vector>
 
 #include "../../include/atsc_gpu.h"
+
+// i32 arithmetic of the reference's release build: wrapping add / sub / mul (a hostile index file can
+// hold any numbers); the one quotient that would trap, INT32_MIN / -1, is defined as INT32_MIN
+static inline int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+static inline int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+static inline int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+static inline int32_t wdiv(int32_t a, int32_t b) { return (a == INT32_MIN && b == -1) ? INT32_MIN : a / b; }
 
 struct atsc_vsri {
     int32_t min_ts = 0, max_ts = 0;
@@ -31,7 +39,7 @@ struct atsc_vsri {
     int32_t sample_count() const {  // lib.rs:368-371
         int32_t c[4];
         current(c);
-        return c[3] + c[1];
+        return wadd(c[3], c[1]);
     }
 };
 
@@ -55,7 +63,7 @@ int atsc_vsri_update_for_point(atsc_vsri *v, int32_t y) {
     int32_t last[4];
     v->current(last);
     auto fake = [&]() {  // lib.rs:393-400 create_fake_segment
-        int32_t s[4] = {0, last[1] + last[3], y, 1};
+        int32_t s[4] = {0, wadd(last[1], last[3]), y, 1};
         v->seg.insert(v->seg.end(), s, s + 4);
     };
     if (v->seg.empty()) {
@@ -66,15 +74,16 @@ int atsc_vsri_update_for_point(atsc_vsri *v, int32_t y) {
     if (last[0] == 0) {
         // lib.rs:375-388 generate_segment: the second point of a segment fixes its rate
         int32_t *s = v->at(v->n() - 1);
-        s[0] = y - last[2];
+        s[0] = wsub(y, last[2]);
         s[3] = 2;
         return 0;
     }
     // lib.rs:410-428 fits_segment: the point must be the next one on the line
-    const int32_t b = last[2] - last[0] * last[1];
-    const int32_t x = (y - b) / last[0];
-    if (x == last[3] + last[1]) {
-        v->at(v->n() - 1)[3] += 1;
+    const int32_t b = wsub(last[2], wmul(last[0], last[1]));
+    const int32_t x = wdiv(wsub(y, b), last[0]);
+    if (x == wadd(last[3], last[1])) {
+        int32_t *s = v->at(v->n() - 1);
+        s[3] = wadd(s[3], 1);
         return 0;
     }
     fake();
@@ -90,10 +99,10 @@ uint64_t atsc_vsri_segment_count(const atsc_vsri *v) { return v->n(); }
 int atsc_vsri_get_sample(const atsc_vsri *v, int32_t y, int32_t *x) {
     for (size_t i = 0; i < v->n(); i++) {
         const int32_t *s = v->at(i);
-        const int32_t end = s[2] + s[0] * (s[3] - 1);
+        const int32_t end = wadd(s[2], wmul(s[0], wsub(s[3], 1)));
         if (y >= s[2] && y <= end) {
             if (s[0] == 0) return 0;  // a one-point segment: the reference divides by zero (panic)
-            *x = (y - (s[2] - s[0] * s[1])) / s[0];
+            *x = wdiv(wsub(y, wsub(s[2], wmul(s[0], s[1]))), s[0]);
             return 1;
         }
     }
@@ -115,8 +124,8 @@ int atsc_vsri_get_time(const atsc_vsri *v, int32_t x, int32_t *y) {
     }
     for (size_t i = 0; i < v->n(); i++) {
         const int32_t *s = v->at(i);
-        if (x >= s[1] && x < s[1] + s[3]) {
-            *y = s[2] + s[0] * x;
+        if (x >= s[1] && x < wadd(s[1], s[3])) {
+            *y = wadd(s[2], wmul(s[0], x));
             return 1;
         }
     }
@@ -148,7 +157,7 @@ int atsc_vsri_get_previous_sample(const atsc_vsri *v, int32_t y, int32_t *x) {
     for (size_t i = 0; i < v->n(); i++) {
         const int32_t *s = v->at(i);
         if (y < s[2]) {
-            *x = s[1] - 1;
+            *x = wsub(s[1], 1);
             return 1;
         }
     }
@@ -165,7 +174,7 @@ int atsc_vsri_is_empty(const atsc_vsri *v, int32_t t0, int32_t t1) {
     int32_t prev_end = 0;
     for (size_t i = 0; i < v->n(); i++) {
         const int32_t *s = v->at(i);
-        const int32_t end = s[2] + s[0] * (s[3] - 1);
+        const int32_t end = wadd(s[2], wmul(s[0], wsub(s[3], 1)));
         if (i >= 1 && t0 > prev_end && t1 < s[2]) return 1;
         if ((t0 >= s[2] && t0 < end) || (t1 < end && t1 >= s[2])) return 0;
         if (t0 < s[2] && t1 > end) return 0;
@@ -179,8 +188,10 @@ uint64_t atsc_vsri_all_timestamps(const atsc_vsri *v, int32_t *out, uint64_t cap
     uint64_t k = 0;
     for (size_t i = 0; i < v->n(); i++) {
         const int32_t *s = v->at(i);
-        for (int32_t f = 0; f < s[3]; f++, k++)
-            if (out && k < cap) out[k] = f * s[0] + s[2];
+        const uint64_t cnt = s[3] > 0 ? (uint64_t)s[3] : 0;
+        const uint64_t room = (out && k < cap) ? cap - k : 0;  // only what fits is generated: a hostile count costs nothing
+        for (uint64_t f = 0; f < cnt && f < room; f++) out[k + f] = wadd(wmul((int32_t)f, s[0]), s[2]);
+        k += cnt;
     }
     return k;
 }
