@@ -34,7 +34,7 @@ API_SYMBOLS = [
     "atsc_vsri_to_text", "atsc_vsri_from_text",
 ]
 KERNEL_NAMES = ["stats", "poly", "rle", "fft_fwd", "select", "emit", "decode", "host_issue", "fft_small", "fft",
-                "reserved10", "reserved11"]
+                "front", "reserved11"]
 
 
 class AtscError(RuntimeError):

@@ -70,6 +70,10 @@ struct Engine {
     size_t samples_cap = 0;
     FftEntry *d_arena = nullptr;
     size_t arena_cap = 0;
+    uint32_t *d_items = nullptr, *h_items = nullptr;  // frames of the wave that go through k_front
+    size_t items_cap = 0;
+    float4 *d_fold = nullptr;  // probe folds of the wave (k_front -> k_fft_fwd)
+    size_t fold_cap = 0;
     float2 *d_spec_xd = nullptr;  // per-frame half spectra of the wave (k_fft_fwd -> k_fft)
     uint32_t *d_spec_keys = nullptr;
     size_t spec_xd_cap = 0, spec_keys_cap = 0;
@@ -85,7 +89,7 @@ struct Engine {
     uint32_t *d_status = nullptr, *h_status = nullptr;
     size_t status_cap = 0;
     // CUDA events around every kernel of the wave (kernel_ms)
-    cudaEvent_t ev[12] = {};  // 0-7 compress pipeline, 8-9 decode, 10-11 between the FFT kernels
+    cudaEvent_t ev[14] = {};  // 0-7 compress pipeline, 8-9 decode, 10-11 between the FFT kernels, 12-13 k_front
     WaveJob job;
     bool dec_active = false;  // a decode wave is pending on this engine
     uint32_t dec_pos = 0, dec_n = 0;
@@ -95,6 +99,7 @@ struct Device {
     int id = 0;
     cudaStream_t st = nullptr;  // setup stream (tables)
     int n_engines = 0, sms = 0;
+    bool front = true;  // k_front (front.cuh) takes the big frames; ATSC_FRONT=0 keeps the separate passes
     Engine eng[MAX_ENGINES];
     uint64_t wave_samples = 0;
     double *inv_d2 = nullptr;
@@ -112,7 +117,7 @@ struct Device {
     // CUDA-event time of every kernel (ms accumulated since reset):
     // 0 stats, 1 plan+poly, 2 rle, 3 fft_fwd, 4 noop+select+scan, 5 emit, 6 decode,
     // 7 HOST time spent preparing and launching waves (not a kernel: shows when a call is host bound),
-    // 8 fft_small, 9 fft (top-k + refinement loop)
+    // 8 fft_small, 9 fft (top-k + refinement loop), 10 front (fused stats + first polynomial step + probe fold)
     double ms[12] = {};
     std::string err;
 };
@@ -387,6 +392,7 @@ int device_init(Device &D) {
     // waves in flight per device and samples per wave (tunable for experiments)
     D.n_engines = env_int("ATSC_ENGINES", 4, 1, MAX_ENGINES);
     D.wave_samples = (uint64_t)env_int("ATSC_WAVE_MI", 72, 1, 512) << 20;
+    D.front = env_int("ATSC_FRONT", 1, 0, 1) != 0;
     D.sms = sms;
     if ((rc = engine_init(D, D.eng[0], sms))) return rc;  // the others are set up when a call first needs them
     CK(cudaEventCreate(&D.ev_begin));
@@ -408,10 +414,11 @@ void device_free(Device &D) {
         void *ptrs[] = {P.rle_k0, P.rle_k1, P.rle_i0, P.rle_i1, P.rle_bnd, P.fft_W, P.fft_Xd, P.fft_keys, P.fft_rank,
                         P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.poly_slope, P.dec_pts,
                         P.dec_mark, P.dec_idx, E.queues, E.d_ctl, E.d_frames, E.d_samples, E.d_arena, E.d_payload,
-                        E.d_dec, E.d_pay_in, E.d_out, E.d_status, E.d_spec_xd, E.d_spec_keys, E.d_chunks, E.d_parts};
+                        E.d_dec, E.d_pay_in, E.d_out, E.d_status, E.d_spec_xd, E.d_spec_keys, E.d_chunks, E.d_parts,
+                        E.d_items, E.d_fold};
         for (void *p : ptrs)
             if (p) cudaFree(p);
-        void *hp[] = {E.h_ctl, E.h_frames, E.h_dec, E.h_status, E.h_chunks};
+        void *hp[] = {E.h_ctl, E.h_frames, E.h_dec, E.h_status, E.h_chunks, E.h_items};
         for (void *p : hp)
             if (p) cudaFreeHost(p);
         for (auto &ev : E.ev)
@@ -479,13 +486,26 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     uint64_t arena = 0, spec = 0, samples = 0;
     bool any_noop = false, any_small = false, any_large = false;
     uint32_t small_lmax = 2;
-    size_t n_chunks = 0;
-    for (uint32_t i = 0; i < n; i++) n_chunks += (reqs[i].len + STATS_CHUNK - 1) / STATS_CHUNK;
+    // frames k_front takes: long enough, and 16-byte aligned pairs (bulk copies, double2 reads)
+    const bool base_ok = D.front && ((uintptr_t)d_samples & 15u) == 0;
+    auto front_frame = [&](const FrameReq &r) {
+        return base_ok && r.len >= FRONT_MIN_SAMPLES && (r.len & 1u) == 0 && (r.off & 1ull) == 0;
+    };
+    size_t n_chunks = 0, n_items = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (front_frame(reqs[i]))
+            n_items++;
+        else
+            n_chunks += (reqs[i].len + STATS_CHUNK - 1) / STATS_CHUNK;
+    }
     hcap = E.chunks_cap;
     if ((rc = grow(D, E.st, E.d_chunks, E.chunks_cap, n_chunks))) return rc;
     if ((rc = grow(D, E.st, E.h_chunks, hcap, E.chunks_cap, true))) return rc;
     if ((rc = grow(D, E.st, E.d_parts, E.parts_cap, n_chunks))) return rc;
-    uint32_t nc = 0;
+    hcap = E.items_cap;
+    if ((rc = grow(D, E.st, E.d_items, E.items_cap, n_items))) return rc;
+    if ((rc = grow(D, E.st, E.h_items, hcap, E.items_cap, true))) return rc;
+    uint32_t nc = 0, ni = 0, nfold = 0;
     for (uint32_t i = 0; i < n; i++) {
         FrameWork &f = E.h_frames[i];
         memset(&f, 0, sizeof f);
@@ -499,7 +519,16 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
         f.geom = -1;
         f.spec_off = ~0ull;
         f.chunk0 = nc;
-        for (uint32_t c0 = 0; c0 < r.len; c0 += STATS_CHUNK) E.h_chunks[nc++] = ChunkRef{i, c0};
+        if (front_frame(r)) {
+            f.front_mode = FM_ON;
+            // the first Polynomial step is worth evaluating when the bounded Catmull-Rom loop will run
+            if (r.bounded && !r.select_only &&
+                (r.comp == C_POLY || (r.comp == C_AUTO && (r.forced == 0xFF || r.forced == C_POLY))))
+                f.front_mode |= FM_POLY;
+            E.h_items[ni++] = i;
+        } else {
+            for (uint32_t c0 = 0; c0 < r.len; c0 += STATS_CHUNK) E.h_chunks[nc++] = ChunkRef{i, c0};
+        }
         samples += r.len;
         uint8_t eff = (r.comp == C_AUTO && r.forced != 0xFF) ? r.forced : r.comp;
         any_noop |= r.comp == C_NOOP;
@@ -516,9 +545,16 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
                     return rc;
                 }
                 f.geom = gi;
-                if (D.geoms_host[gi].T4) {
+                const FftGeom &G = D.geoms_host[gi];
+                if (G.T4) {
                     f.spec_off = spec;
-                    spec += D.geoms_host[gi].M + 8;
+                    spec += G.M + 8;
+                    // Auto frames that k_front streams also get the probe's stage-1 fold there
+                    if ((f.front_mode & FM_ON) && r.bounded && r.comp == C_AUTO && r.forced == 0xFF && !r.select_only &&
+                        f2_fold_ra(G.M1) && ((L - r.len) / 2) % 2 == 0) {
+                        f.front_mode |= FM_FOLD;
+                        f.fold_idx = nfold++;
+                    }
                 }
             }
             uint32_t mf = std::max<uint32_t>(3, r.len / 100);
@@ -529,6 +565,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
             arena += cap;
         }
     }
+    if ((rc = grow(D, E.st, E.d_fold, E.fold_cap, (size_t)nfold * FRONT_FOLD_SLOTS + 1))) return rc;
     if ((rc = sync_geoms(D))) return rc;
     if ((rc = grow(D, E.st, E.d_arena, E.arena_cap, (size_t)arena + 1))) return rc;
     if ((rc = grow(D, E.st, E.d_spec_xd, E.spec_xd_cap, (size_t)spec + 1))) return rc;
@@ -538,11 +575,21 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     if ((rc = grow(D, E.st, E.d_payload, E.payload_cap, (size_t)std::max<uint64_t>(samples, 1u << 20) + 64 * (size_t)n))) return rc;
     cudaStream_t st = E.st;
     CK(cudaMemcpyAsync(E.d_frames, E.h_frames, (size_t)n * sizeof(FrameWork), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(E.d_chunks, E.h_chunks, n_chunks * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
+    if (n_chunks) CK(cudaMemcpyAsync(E.d_chunks, E.h_chunks, n_chunks * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
+    if (n_items) CK(cudaMemcpyAsync(E.d_items, E.h_items, n_items * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(E.queues, 0, 64 * sizeof(unsigned), st));
     CK(cudaMemsetAsync(E.d_ctl, 0, sizeof(WaveCtl), st));
+    CK(cudaEventRecord(E.ev[12], st));
+    if (n_items) {
+        launch_front(E.d_frames, E.d_items, (uint32_t)n_items, d_samples, max_err, D.geoms_dev, E.d_fold, E.queues + 9, st);
+        D.launches++;
+    }
+    CK(cudaEventRecord(E.ev[13], st));
     CK(cudaEventRecord(E.ev[0], st));
-    launch_stats(E.d_frames, E.d_chunks, (uint32_t)n_chunks, d_samples, E.d_parts, E.queues + 0, st);
+    if (n_chunks) {
+        launch_stats(E.d_frames, E.d_chunks, (uint32_t)n_chunks, d_samples, E.d_parts, E.queues + 0, st);
+        D.launches++;
+    }
     CK(cudaEventRecord(E.ev[1], st));
     launch_plan(E.d_frames, n, d_samples, E.d_parts, st);
     launch_poly(E.d_frames, n, d_samples, max_err, D.inv_d2, E.pool, E.queues + 1, st);
@@ -553,7 +600,8 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     }
     CK(cudaEventRecord(E.ev[10], st));
     if (spec) {
-        launch_fft_fwd(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_spec_xd, E.d_spec_keys, E.queues + 7, st);
+        launch_fft_fwd(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_spec_xd, E.d_spec_keys, E.d_fold,
+                       E.queues + 7, st);
         D.launches++;
     }
     CK(cudaEventRecord(E.ev[11], st));
@@ -565,7 +613,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     // RLE last: its sort runs only for frames where a size lower bound still beats Polynomial and FFT
     launch_rle(E.d_frames, n, d_samples, max_err, E.pool, E.queues + 2, st);
     CK(cudaEventRecord(E.ev[4], st));
-    D.launches += 4;
+    D.launches += 3;
     if (any_noop) {
         launch_noop_size(E.d_frames, n, d_samples, E.queues + 4, st);
         D.launches++;
@@ -602,6 +650,8 @@ int wait_wave(Device &D, Engine &E, uint32_t n, const double *d_samples, uint64_
     float te = 0.f;
     CK(cudaEventElapsedTime(&te, E.ev[6], E.ev[7]));
     D.ms[5] += te;
+    CK(cudaEventElapsedTime(&te, E.ev[12], E.ev[13]));
+    D.ms[10] += te;
     const uint64_t total = E.h_ctl->total;
     *payload_total = total;
     if (E.h_ctl->overflow) {

@@ -18,6 +18,12 @@ constexpr int BLOCK = 1024;            // threads per CTA for the per-frame kern
 
 constexpr uint8_t TIE_FFT_LOOP = 1, TIE_POLY_LOOP = 2, TIE_SELECT = 4, TIE_FFT_TOPK = 8;
 
+// FrameWork.front_mode: the frame goes through k_front (stats in the streaming pass); it also evaluates
+// the first Polynomial step there; it also accumulates the FFT probe's stage-1 fold there
+constexpr uint8_t FM_ON = 1, FM_POLY = 2, FM_FOLD = 4;
+// FrameWork.front_res: poly_step / poly_err hold the first step's error (the loop did not end there)
+constexpr uint8_t FRES_POLY1 = 1;
+
 // One record per frame, lives in device memory for the duration of a wave.
 struct FrameWork {
     // ---- input
@@ -43,7 +49,8 @@ struct FrameWork {
     uint32_t rle_groups, rle_size;
     uint8_t rle_valid;
     uint8_t fft_small;  // transform length <= 1152: k_fft_small (fft_small.cuh) runs the FFT candidate
-    uint8_t pad1[2];
+    uint8_t front_mode;  // FM_* bits: what k_front (front.cuh) does for this frame (set by the host)
+    uint8_t front_res;   // FRES_* bits: what k_front left behind
     // ---- fft candidate
     uint32_t fft_count, fft_size;
     uint16_t fft_iters;
@@ -55,7 +62,7 @@ struct FrameWork {
     uint32_t aux_size;   // Noop / Constant payload size
     uint32_t fwd_done;   // k_fft_fwd left the half spectrum + keys at spec_off
     uint32_t chunk0;     // first entry of this frame in the wave's stats chunk table
-    uint32_t pad3;
+    uint32_t fold_idx;   // FM_FOLD frames: slot in the wave's fold arena
     uint64_t spec_off;   // entry offset into the wave's spectrum arena (~0 = frame not eligible for fft2.cuh)
     // ---- result
     uint8_t winner, near_tie;

@@ -58,6 +58,13 @@ struct FftGeom {
     const float2 *T4T;  // [M1][M2] the same table, row-major (inverse, fft2.cuh)
 };
 
+// radix RA of pass-1 stage 1 when the geometry has a probe (fft2.cuh: M = M1 x 243 with
+// M1 = RA * RB in {288, 144, 72, 36}), else 0.  The probe's stage-1 sums are folds over RA
+// contiguous chunks of RB * 243 complex elements, which k_front (front.cuh) accumulates.
+__host__ __device__ inline uint32_t f2_fold_ra(uint32_t M1) {
+    return M1 == 288u || M1 == 144u ? 16u : M1 == 72u ? 8u : M1 == 36u ? 4u : 0u;
+}
+
 // per-CTA-slot global workspace
 struct FftWs {
     float2 *W;       // [Mmax]   four-step intermediate / permuted spectrum

@@ -28,6 +28,11 @@ constexpr int F2_SMEM_BYTES = F2_SMEM_F2 * (int)sizeof(float2);  // 73,984 B
 // exp(-+ 2 pi i j / R) as immediates (j is a compile-time constant after unrolling)
 template <int R, bool INV>
 __device__ __forceinline__ float2 root_c(int j) {
+    if (R == 4) {
+        constexpr float C[4] = {1.0f, 0.0f, -1.0f, 0.0f};
+        constexpr float S[4] = {0.0f, 1.0f, 0.0f, -1.0f};
+        return make_float2(C[j], INV ? S[j] : -S[j]);
+    }
     if (R == 8) {
         constexpr float C[8] = {1.0f, 0.707106781186548f, 0.0f, -0.707106781186547f, -1.0f, -0.707106781186548f, 0.0f, 0.707106781186547f};
         constexpr float S[8] = {0.0f, 0.707106781186547f, 1.0f, 0.707106781186548f, 0.0f, -0.707106781186547f, -1.0f, -0.707106781186548f};
@@ -133,6 +138,34 @@ struct DftS<27, S, INV> {
     static __device__ __forceinline__ void run(float2 *a) { dft_comp<3, 9, S, INV>(a); }
 };
 
+// ---------------------------------------------------------------------------------------
+// The two stage-1 outputs the PROBE needs (q = 1 and q = RA-1 of the radix-RA butterfly over
+// a[t] = z[t * RB*243 + m] = r_t + i q_t) are DEFINED through two sequential folds over t = 0 .. RA-1,
+//     A = sum_t r_t w^t,   B = sum_t q_t w^t,   w = exp(-2 pi i / RA)      (one fold_acc per term),
+//     s_1 = A + i B,       s_{RA-1} = conj(A) + i conj(B)                   (fold_out).
+// The chunks t are CONTIGUOUS pieces of the padded frame, so k_front (front.cuh) accumulates A and
+// B while the frame streams through shared memory once; the full transform and the stand-alone
+// probe below evaluate the same expressions, so the bins of the probed rows are bit-identical
+// wherever they are computed.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void fold_acc(float4 &ab, float r, float q, float2 w) {
+    ab.x = fmaf(r, w.x, ab.x);
+    ab.y = fmaf(r, w.y, ab.y);
+    ab.z = fmaf(q, w.x, ab.z);
+    ab.w = fmaf(q, w.y, ab.w);
+}
+__device__ __forceinline__ void fold_out(float4 ab, float2 &s1, float2 &sR) {
+    s1 = make_float2(__fsub_rn(ab.x, ab.w), __fadd_rn(ab.y, ab.z));
+    sR = make_float2(__fadd_rn(ab.x, ab.w), __fsub_rn(ab.z, ab.y));
+}
+template <int RA>
+__device__ __forceinline__ void fold_pair(const float2 *a, float2 &s1, float2 &sR) {
+    float4 ab = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < RA; t++) fold_acc(ab, a[t].x, a[t].y, root_c<RA, false>(t));
+    fold_out(ab, s1, sR);
+}
+
 // padded ("gibbs sized") complex element n of the frame: (x[2n], x[2n+1]) as f32 (fft.rs:184-228).
 // `vec`: d + (2n - prefix) is 16-byte aligned for every n, so interior elements take one 128-bit load.
 __device__ __forceinline__ float2 f2_load_z(const double *__restrict__ d, int N, int prefix, int n, bool vec) {
@@ -164,7 +197,16 @@ __device__ inline void f2_pass1(const double *__restrict__ d, int N, int prefix,
             float2 a[RA];
 #pragma unroll
             for (int t = 0; t < RA; t++) a[t] = f2_load_z(d, N, prefix, (p + RB * t) * F2_M2 + c0 + lc, vec);
-            DftS<RA, 1, false>::run(a);
+            if (RA >= 4) {
+                // outputs 1 and RA-1 feed the probed rows: sequential folds (see fold_step)
+                float2 s1, sR;
+                fold_pair<RA>(a, s1, sR);
+                DftS<RA, 1, false>::run(a);
+                a[1] = s1;
+                a[RA - 1] = sR;
+            } else {
+                DftS<RA, 1, false>::run(a);
+            }
             float2 *y = sm + lc * P1 + RA * p;
             y[0] = a[0];
 #pragma unroll
@@ -344,10 +386,11 @@ __device__ inline void f2_probe_pass1(const double *__restrict__ d, int N, int p
         float2 a[RA];
 #pragma unroll
         for (int t = 0; t < RA; t++) a[t] = f2_load_z(d, N, prefix, (p + RB * t) * F2_M2 + c, vec);
-        DftS<RA, 1, false>::run(a);  // only outputs 1 and RA-1 are used: the rest is dead code
+        float2 s1, sR;
+        fold_pair<RA>(a, s1, sR);  // only outputs 1 and RA-1 are needed
         float2 *y = sm + c * P1;
-        y[p] = cmul(a[1], __ldg(tw1 + p));
-        y[RB + p] = cmul(a[RA - 1], __ldg(tw1 + p * (RA - 1)));
+        y[p] = cmul(s1, __ldg(tw1 + p));
+        y[RB + p] = cmul(sR, __ldg(tw1 + p * (RA - 1)));
     }
     __syncthreads();
     for (int item = tid; item < 2 * F2_M2; item += nth) {
@@ -571,6 +614,47 @@ __device__ inline uint32_t f2_probe(const double *__restrict__ d, int N, int pre
         case 144: f2_probe_pass1<16, 9>(d, N, prefix, g.tw1, g.T4, W, sm); RA = 16; break;
         case 72: f2_probe_pass1<8, 9>(d, N, prefix, g.tw1, g.T4, W, sm); RA = 8; break;
         case 36: f2_probe_pass1<4, 9>(d, N, prefix, g.tw1, g.T4, W, sm); RA = 4; break;
+        default: return 0u;
+    }
+    return f2_probe_pass2((int)g.M1, RA, g.tw2, g.twL1, g.twL2, W, sm);
+}
+
+// ---------------------------------------------------------------------------------------
+// PROBE from a stored fold: k_front (front.cuh) leaves the two folds (A, B) of every slot
+// m = p*243 + c < RB*243 as one float4  fold[m] = (A.x, A.y, B.x, B.y).  What remains is fold_out,
+// the Stockham twiddle, pass-1 stage 2 for the two families and pass 2 for the 2*RB probed rows.
+// ---------------------------------------------------------------------------------------
+template <int RA, int RB>
+__device__ inline void f2_fold_stage2(const float4 *__restrict__ fold, const float2 *__restrict__ tw1,
+                                      const float2 *__restrict__ T4, float2 *Wp) {
+    constexpr int M1 = RA * RB;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int item = tid; item < 2 * F2_M2; item += nth) {
+        const int fam = item & 1, c = item >> 1;  // fam 0: q = 1, fam 1: q = RA-1
+        const int q = fam ? RA - 1 : 1;
+        float2 b[RB];
+#pragma unroll
+        for (int t = 0; t < RB; t++) {
+            float2 s1, sR;
+            fold_out(__ldcg(fold + t * F2_M2 + c), s1, sR);
+            b[t] = cmul(fam ? sR : s1, __ldg(tw1 + t * q));
+        }
+        DftS<RB, 1, false>::run(b);
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            const int k1 = q + RA * u, lr = fam ? RB + (RB - 1 - u) : u;
+            __stcg(Wp + c * (2 * RB) + lr, cmul(b[u], __ldg(T4 + c * M1 + k1)));
+        }
+    }
+    __syncthreads();
+}
+__device__ inline uint32_t f2_probe_from_fold(const float4 *__restrict__ fold, const FftGeom &g, float2 *W, float2 *sm) {
+    int RA;
+    switch (g.M1) {
+        case 288: f2_fold_stage2<16, 18>(fold, g.tw1, g.T4, W); RA = 16; break;
+        case 144: f2_fold_stage2<16, 9>(fold, g.tw1, g.T4, W); RA = 16; break;
+        case 72: f2_fold_stage2<8, 9>(fold, g.tw1, g.T4, W); RA = 8; break;
+        case 36: f2_fold_stage2<4, 9>(fold, g.tw1, g.T4, W); RA = 4; break;
         default: return 0u;
     }
     return f2_probe_pass2((int)g.M1, RA, g.tw2, g.twL1, g.twL2, W, sm);

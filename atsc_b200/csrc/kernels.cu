@@ -5,8 +5,12 @@
 // Pipeline per wave (compress):  stats -> plan -> poly -> rle -> fft -> select -> scan -> emit
 // Reference citations are relative to /root/reference/atsc/src/.
 #include "kernels.h"
+
+#include <cstdio>
+#include <cstdlib>
 #include "fft2.cuh"
 #include "fft_small.cuh"
+#include "front.cuh"
 #include "poly.cuh"
 #include "stats.cuh"
 #include "varscan.cuh"
@@ -60,40 +64,51 @@ __global__ void k_plan(FrameWork *fr, uint32_t n, const double *__restrict__ sam
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     FrameWork *fw = &fr[i];
+    if (fw->front_mode & FM_ON) return;  // k_front finished this frame's stats and plan
     finish_stats(samples + fw->off, fw->len, parts + fw->chunk0, (fw->len + STATS_CHUNK - 1) / STATS_CHUNK, fw);
-    uint8_t np = 0, nr = 0, nf = 0, pt = 0;
-    switch (fw->comp) {
-        case C_AUTO:
-            if (fw->select_only || (!fw->is_const && fw->forced == 0xFF))
-                np = nr = nf = 1;
-            else if (!fw->is_const) {
-                // frame/mod.rs:106-111: the sampled pass chose; compress everything with it
-                nf = fw->forced == C_FFT;
-                np = fw->forced == C_POLY;
-                nr = fw->forced == C_RLE;
-            }
-            break;
-        case C_FFT: nf = 1; break;
-        case C_POLY: np = 1; break;
-        case C_IDW:
-            np = 1;
-            pt = 1;
-            break;
-        case C_RLE: nr = 1; break;
-        default: break;
+    plan_frame(fw);
+}
+
+// Fused front end of the big frames (front.cuh): stats + first Polynomial step + FFT probe fold in
+// ONE pass over the samples, staged through shared memory by bulk asynchronous copies.
+__global__ void __launch_bounds__(FR_CTA, 1) k_front(FrameWork *fr, const uint32_t *__restrict__ items, uint32_t n_items,
+                                                        const double *__restrict__ samples, double max_err,
+                                                        const FftGeom *__restrict__ geoms, float4 *fold_arena, unsigned *q, uint32_t dbg) {
+    extern __shared__ __align__(128) unsigned char dyn_front[];
+    FrontSmem *sm = reinterpret_cast<FrontSmem *>(dyn_front);
+    uint32_t fill = 0, use = 0;
+    FrontFeed feed;
+    feed.d = samples;
+    feed.N = feed.ntiles = feed.issued = 0;
+    if (threadIdx.x == FR_PRODUCER) {
+        for (uint32_t s = 0; s < FR_SLOTS; s++) {
+            mbar_init(&sm->full[s], 1u);
+            mbar_init(&sm->empty[s], FR_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int first = (int)atomicAdd(q, 1u);
+        sm->item = first;
+        if (first < (int)n_items) {
+            const FrameWork *nf = &fr[items[first]];
+            feed.d = samples + nf->off;
+            feed.N = nf->len;
+            feed.ntiles = (feed.N + FR_TILE - 1u) / FR_TILE;
+        }
     }
-    fw->need_poly = np;
-    fw->need_rle = nr;
-    fw->need_fft = nf;
-    fw->poly_type = pt;
-    fw->poly_valid = fw->rle_valid = fw->fft_valid = 0;
-    fw->poly_size = fw->rle_size = fw->fft_size = 0;
-    fw->poly_err = fw->fft_err = 0.0;
-    fw->poly_tie = fw->fft_tie = 0;
-    fw->poly_iters = fw->fft_iters = 0;
-    fw->fft_count = 0;
-    fw->aux_size = 0;
-    fw->fwd_done = 0;
+    __syncthreads();
+    FrontProf prof;
+    for (;;) {
+        const int it = sm->item;  // the producer claims the next item while a frame's tail runs (front_frame)
+        if (it >= (int)n_items) break;
+        front_frame(fr, items, n_items, it, samples, max_err, geoms, fold_arena, q, sm, fill, use, feed, prof, dbg);
+    }
+#ifdef FRONT_PROF
+    if (threadIdx.x == FR_PRODUCER && blockIdx.x == 77) printf("k_front cta 77 producer: issue cycles %lld\n", prof.issue);
+    if (threadIdx.x == 0 && blockIdx.x == 77) printf("k_front cta 77: arrival skew (max - min) total %lld; last warp 15: %lld, 14: %lld, other: %lld\n", prof.skew, prof.last15, prof.last14, prof.lastother);
+    if ((threadIdx.x == 0 || threadIdx.x == 288) && (blockIdx.x == 0 || blockIdx.x == 77))
+        printf("k_front cta %d thr %d: frames %lld tiles %lld | cycles head %lld wait_full %lld pass_a %lld barrier %lld pass_b %lld (trips %lld x %lld, syncwarp %lld) tail %lld | parked %lld\n",
+               blockIdx.x, threadIdx.x, prof.frames, prof.tiles, prof.head, prof.wait_full, prof.pass_a, prof.barrier, prof.pass_b, prof.ntrips, prof.ntrips ? prof.trips / prof.ntrips : 0, prof.syncw, prof.tail, prof.parked);
+#endif
 }
 
 // =========================================================================================
@@ -110,7 +125,7 @@ __global__ void __launch_bounds__(512, 2) k_poly(FrameWork *fr, uint32_t n, cons
         int i = queue_next(q, &s_item);
         if (i >= (int)n) break;
         FrameWork *fw = &fr[i];
-        if (!fw->need_poly) continue;
+        if (!fw->need_poly || fw->poly_valid) continue;  // poly_valid: k_front settled it at the first step
         poly_frame(samples + fw->off, fw, max_err, inv_d2, shd, ws);
     }
 }
@@ -415,7 +430,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fft_small(FrameWork *fr, uint32_
 __global__ void __launch_bounds__(F2_THREADS, 2) k_fft_fwd(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
                                                            double max_err, const FftGeom *__restrict__ geoms,
                                                            SlotPool pool, float2 *spec_xd, uint32_t *spec_keys,
-                                                           unsigned *q) {
+                                                           const float4 *__restrict__ fold_arena, unsigned *q) {
     extern __shared__ float2 dyn_f2[];
     __shared__ uint32_t sh[40];
     __shared__ FftGeom sg;
@@ -448,7 +463,10 @@ __global__ void __launch_bounds__(F2_THREADS, 2) k_fft_fwd(FrameWork *fr, uint32
             const uint32_t mf = (3 >= N / 100) ? 3 : N / 100;
             const uint32_t cap = min(fw->fft_list_cap, (uint32_t)FFT_KCAP);
             const uint32_t smax = sg.Bn > 65536u ? 502u : 251u;
-            uint32_t nz = block_sum_u32(f2_probe(samples + fw->off, (int)N, (int)prefix, sg, W, dyn_f2), sh);
+            // frames that went through k_front bring the probe's stage-1 fold with them: no sample is read
+            uint32_t nz = (fw->front_mode & FM_FOLD)
+                              ? block_sum_u32(f2_probe_from_fold(fold_arena + (size_t)fw->fold_idx * FR_FOLD_SLOTS, sg, W, dyn_f2), sh)
+                              : block_sum_u32(f2_probe(samples + fw->off, (int)N, (int)prefix, sg, W, dyn_f2), sh);
             uint32_t c1 = min(min(mf, nz), cap);
             bool pruned = fft_payload_size(c1, min(c1, smax)) > bound;
             if (!pruned) {
@@ -1113,6 +1131,8 @@ int kernels_init() {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, FRONT_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_fft_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_fft_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs_smem_bytes(FS_LMAX));
@@ -1150,9 +1170,16 @@ void launch_fft_small(FrameWork *fr, uint32_t n, const double *samples, double m
     k_fft_small<<<grid_for(n, 8 * sms()), FS_THREADS, fs_smem_bytes(lmax), st>>>(fr, n, samples, max_err, geoms, arena, lmax, q);
 }
 void launch_fft_fwd(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
-                    SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st) {
+                    SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, const float4 *fold_arena, unsigned *q,
+                    cudaStream_t st) {
     k_fft_fwd<<<grid_for(n, pool.fwd_slots), F2_THREADS, F2_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool,
-                                                                             spec_xd, spec_keys, q);
+                                                                             spec_xd, spec_keys, fold_arena, q);
+}
+void launch_front(FrameWork *fr, const uint32_t *items, uint32_t n_items, const double *samples, double max_err,
+                  const FftGeom *geoms, float4 *fold_arena, unsigned *q, cudaStream_t st) {
+    static const uint32_t dbg = getenv("ATSC_FRONT_DBG") ? (uint32_t)atoi(getenv("ATSC_FRONT_DBG")) : 0u;  // timing experiments
+    k_front<<<grid_for(n_items, sms()), FR_CTA, FRONT_SMEM_BYTES, st>>>(fr, items, n_items, samples, max_err, geoms,
+                                                                            fold_arena, q, dbg);
 }
 void launch_noop_size(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st) {
     k_noop_size<<<grid_for(n, 2 * sms()), BLOCK, 0, st>>>(fr, n, samples, q);

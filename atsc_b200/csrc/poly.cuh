@@ -131,6 +131,43 @@ __device__ __forceinline__ bool poly_tame(double vmin, double vmax) {
     return (vmin >= 1e-200 || vmax <= -1e-200) && fmax(fabs(vmin), fabs(vmax)) <= 1e10;
 }
 
+// The part of a Catmull-Rom step's MAPE sum that the segment loop does not cover: the Linear ends
+// (segment 0, segment K-2 -- possibly irregular -- and the last sample), through the generic
+// per-sample arithmetic.  Returns this thread's share of the sum; all threads call.
+__device__ inline double poly_mape_ends(const double *__restrict__ d, const PolyKeys &k, double vmin, double vmax) {
+    const uint32_t N = k.N, step = k.step, K = k.K, T = blockDim.x, t = threadIdx.x;
+    const double stepd = (double)step;
+    auto pts = [&](uint32_t j) { return d[poly_pos(k, j)]; };
+    double acc = 0.0;
+    const uint32_t Kreg = k.Kreg;
+    const uint32_t last_reg = (Kreg - 1) * step;  // position of the last regular key
+    const uint32_t start_last = (K >= 4) ? (K - 2) * step : 0u;  // K < 4: no Catmull-Rom segment at all
+    const uint32_t nA = min(step, start_last), nB = N - start_last;
+    for (uint32_t e = t; e < nA + nB; e += T) {
+        const uint32_t x = e < nA ? e : start_last + (e - nA);
+        const uint32_t i = x / step, jj = x - i * step;
+        double v;
+        if (x == N - 1) {
+            v = d[N - 1];
+        } else if (i == Kreg - 1) {
+            // irregular last segment [last_reg, N-1]: always Linear (it is segment K-2)
+            double at = (double)last_reg, bt = (double)(N - 1);
+            double nt = __ddiv_rn(__dsub_rn((double)x, at), __dsub_rn(bt, at));
+            v = __dadd_rn(__dmul_rn(d[last_reg], __dsub_rn(1.0, nt)), __dmul_rn(d[N - 1], nt));
+        } else if (i >= 1 && i + 2 < K) {
+            // only reached when K < 4 cannot happen (then no such i exists); kept for completeness
+            v = poly_eval_at(k, x, pts);
+        } else {
+            // first segment, or the regular segment K-2: Linear  a * (1 - t) + b * t
+            const uint32_t pb = (i + 1 < Kreg) ? (i + 1) * step : N - 1;
+            const double nt = __ddiv_rn((double)jj, stepd);
+            v = __dadd_rn(__dmul_rn(d[i * step], __dsub_rn(1.0, nt)), __dmul_rn(d[pb], nt));
+        }
+        acc += mape_term(round_and_limit5_fast(v, vmin, vmax), d[x]);
+    }
+    return acc;
+}
+
 // MAPE (utils/error.rs:104-116) of one candidate step against the frame; block-wide.
 // Catmull-Rom path: identical value arithmetic to poly_eval_at (same operations, same order).
 // Thread t owns one offset j inside the segments (its Hermite basis values stay in registers) and
@@ -212,33 +249,7 @@ __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys 
         }
         for (uint32_t i = nblk * NS + 1 + g; i <= i_hi; i += G) acc += seg_err(i);  // fewer than NS left over
     }
-    // ---- the Linear ends: segment 0, segment K-2 (possibly irregular) and the last sample
-    const uint32_t Kreg = k.Kreg;
-    const uint32_t last_reg = (Kreg - 1) * step;  // position of the last regular key
-    const uint32_t start_last = (K >= 4) ? (K - 2) * step : 0u;  // K < 4: no Catmull-Rom segment at all
-    const uint32_t nA = min(step, start_last), nB = N - start_last;
-    for (uint32_t e = t; e < nA + nB; e += T) {
-        const uint32_t x = e < nA ? e : start_last + (e - nA);
-        const uint32_t i = x / step, jj = x - i * step;
-        double v;
-        if (x == N - 1) {
-            v = d[N - 1];
-        } else if (i == Kreg - 1) {
-            // irregular last segment [last_reg, N-1]: always Linear (it is segment K-2)
-            double at = (double)last_reg, bt = (double)(N - 1);
-            double nt = __ddiv_rn(__dsub_rn((double)x, at), __dsub_rn(bt, at));
-            v = __dadd_rn(__dmul_rn(d[last_reg], __dsub_rn(1.0, nt)), __dmul_rn(d[N - 1], nt));
-        } else if (i >= 1 && i + 2 < K) {
-            // only reached when K < 4 cannot happen (then no such i exists); kept for completeness
-            v = poly_eval_at(k, x, pts);
-        } else {
-            // first segment, or the regular segment K-2: Linear  a * (1 - t) + b * t
-            const uint32_t pb = (i + 1 < Kreg) ? (i + 1) * step : N - 1;
-            const double nt = __ddiv_rn((double)jj, stepd);
-            v = __dadd_rn(__dmul_rn(d[i * step], __dsub_rn(1.0, nt)), __dmul_rn(d[pb], nt));
-        }
-        acc += mape_term(round_and_limit5_fast(v, vmin, vmax), d[x]);
-    }
+    acc += poly_mape_ends(d, k, vmin, vmax);
     double s = block_sum(acc, scratch);
     return __ddiv_rn(s, (double)N);
 }
@@ -367,6 +378,8 @@ __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, d
                     cur = prev_err;  // same keys -> same reconstruction -> same error
                 } else if (step == 1 && it <= 22) {
                     cur = 0.0;  // value unused: the `len == data_len` exit below overrides it
+                } else if (it == 1 && (fw->front_res & FRES_POLY1) && step == fw->poly_step) {
+                    cur = fw->poly_err;  // k_front evaluated this step while it streamed the frame
                 } else {
                     cur = tame ? poly_mape<true>(d, k, ptype, vmin, vmax, inv_d2, ws, sh)
                                : poly_mape<false>(d, k, ptype, vmin, vmax, inv_d2, ws, sh);

@@ -1,0 +1,138 @@
+"""k_front (fused stats + first Polynomial step + FFT probe fold, one read of the frame) against the
+separate passes (ATSC_FRONT=0) and against the CPU oracle: same frame records, same payload bytes.
+Reference behaviour under test: frame/mod.rs:71-149, polynomial.rs:209-277, optimizer/utils.rs:39-89."""
+import os
+
+import numpy as np
+import pytest
+
+import gen
+import oracle_lib as O
+from test_gpu_parity import run_batch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctxs():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import atsc_b200
+    on = atsc_b200.Context()
+    os.environ["ATSC_FRONT"] = "0"
+    try:
+        off = atsc_b200.Context()
+    finally:
+        os.environ.pop("ATSC_FRONT")
+    yield on, off
+    on.close()
+    off.close()
+
+
+def front_frames():
+    """Frames of >= 16384 samples that exercise every branch of the streaming pass."""
+    rng = np.random.default_rng(77)
+    out = []
+    for n in (16384, 32768, 65536, 131072):
+        for k in ("periodic", "gauge", "util", "saw", "noisy", "steps", "constant"):
+            out.append((f"{k}{n}", gen.make(k, n, 300 + n % 89 + len(k))))
+    # even lengths that are not powers of two (no fold, ragged last tile) and one ragged fast geometry
+    for n in (16386, 20000, 70000, 100002, 131070):
+        out.append((f"util{n}", gen.make("util", n, n)))
+        out.append((f"gauge{n}", gen.make("gauge", n, n + 1)))
+    a = gen.make("periodic", 131072, 5)
+    a[:9000] = a[0]                                   # constant tiles first: skipped work -> fallback
+    out.append(("const_prefix", a))
+    a = gen.make("util", 65536, 6)
+    a[:4096] = a[0]
+    out.append(("const_tile0", a))
+    a = gen.make("periodic", 65536, 7) - 100.0         # sign changes: not tame
+    out.append(("signs", a))
+    a = gen.make("util", 131072, 8)
+    a[70000] = 0.0                                     # one zero sample: not tame, MAPE inf
+    out.append(("one_zero", a))
+    a = gen.make("periodic", 131072, 9, )
+    a[::5000] += 400.0                                 # spikes: Catmull-Rom overshoot -> parked samples
+    out.append(("spikes", a))
+    a = np.where(np.arange(65536) % 2000 < 1000, 10.0, 90.0) + rng.normal(0, 0.01, 65536)  # square wave: clamp acts
+    out.append(("square", np.round(a, 3)))
+    a = np.linspace(1.0, 1e6, 131072)                  # trend: the published range moves with every tile
+    out.append(("ramp", np.round(a, 2)))
+    a = np.full(131072, 7.0); a[65535] = 8.0; a[250] = 9.0; a[249] = 9.5
+    out.append(("threshold_runs", a))
+    a = np.arange(131072, dtype=np.float64) % 300
+    out.append(("all_runs", a))
+    a = gen.make("util", 32768, 10); a[5] = np.nan     # NaN sample (frame level API does not clean)
+    out.append(("nan", a))
+    a = gen.make("noisy", 65536, 11) * 1e12            # beyond the tame magnitude
+    out.append(("huge", a))
+    return out
+
+
+def same_records(on, off, names, tag):
+    for name, (a, pa), (b, pb) in zip(names, on, off):
+        what = f"{tag} {name}"
+        assert (a.compressor, a.payload_len, a.iterations) == (b.compressor, b.payload_len, b.iterations), what
+        assert pa == pb, what
+        if np.isfinite(b.error):
+            assert abs(a.error - b.error) <= 1e-12 * max(1.0, abs(b.error)), what
+        else:
+            assert not np.isfinite(a.error) or a.error == b.error, what
+
+
+@pytest.mark.parametrize("comp,err,speed", [
+    (O.AUTO, 0.05, 0), (O.AUTO, 0.01, 0), (O.AUTO, 0.05, 6), (O.AUTO, 0.0, 0),
+    (O.POLYNOMIAL, 0.05, 0), (O.POLYNOMIAL, 0.001, 0), (O.FFT, 0.05, 0), (O.RLE, 0.05, 0), (O.CONSTANT, 0.05, 0),
+])
+def test_front_matches_separate_passes(ctxs, comp, err, speed):
+    on, off = ctxs
+    cs = front_frames()
+    if comp == O.FFT:
+        cs = [c for c in cs if len(c[1]) in (16384, 32768, 65536, 131072)][:12]
+    arrays = [a for _, a in cs]
+    names = [n for n, _ in cs]
+    r_on = run_batch(on, arrays, comp, max_error=err, speed=speed)
+    r_off = run_batch(off, arrays, comp, max_error=err, speed=speed)
+    same_records(r_on, r_off, names, f"{O.NAMES[comp]} e={err} c={speed}")
+    k = on.kernel_ms(reset=True)
+    assert k["front"] > 0.0, "k_front did not run"
+
+
+def test_front_unbounded_and_idw(ctxs):
+    on, off = ctxs
+    cs = [c for c in front_frames() if len(c[1]) == 16384]
+    arrays = [a for _, a in cs]
+    names = [n for n, _ in cs]
+    for comp, bounded in ((O.POLYNOMIAL, False), (O.IDW, True), (O.NOOP, False)):
+        r_on = run_batch(on, arrays, comp, bounded=bounded)
+        r_off = run_batch(off, arrays, comp, bounded=bounded)
+        same_records(r_on, r_off, names, O.NAMES[comp])
+
+
+def test_front_against_oracle(ctxs):
+    """Auto at -e 5: winner, sizes and bytes against the oracle for the streamed frames."""
+    on, _ = ctxs
+    cs = [c for c in front_frames() if not c[0].startswith(("nan",))]
+    arrays = [a for _, a in cs]
+    got = run_batch(on, arrays, O.AUTO, max_error=0.05)
+    bad = []
+    for (name, a), (o, b) in zip(cs, got):
+        wc, wb, _, _ = O.compress_best(a, np.float32(0.05), 0)
+        if o.compressor != wc or (wc != O.FFT and b != wb):
+            if not o.near_tie:
+                bad.append(name)
+    assert not bad, bad
+
+
+def test_front_stats_bytes(ctxs):
+    """RLE / Constant / Polynomial(unbounded) bytes of streamed frames equal the oracle's: the stats
+    (min, max, bitdepth, run counts and their varint classes) are exact."""
+    on, _ = ctxs
+    cs = [c for c in front_frames() if c[0] in ("threshold_runs", "all_runs", "square", "steps131072", "saw65536",
+                                                "gauge32768", "ramp", "signs", "huge")]
+    arrays = [a for _, a in cs]
+    for comp in (O.RLE, O.CONSTANT, O.POLYNOMIAL):
+        got = run_batch(on, arrays, comp, bounded=False)
+        for (name, a), (o, b) in zip(cs, got):
+            assert b == O.compress(comp, a), f"{O.NAMES[comp]} {name}"
