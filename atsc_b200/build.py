@@ -19,7 +19,7 @@ SOURCES = ["kernels.cu", "api.cu", "stream.cpp", "ingest.cpp", "vsri.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "-Xcompiler", "-fPIC",
-] + (["-DFRONT_PROF"] if os.environ.get("ATSC_FRONT_PROF") else []) + [
+
     # f32 FFT may contract to FMA; every f64 value computation that must be bit-exact uses
     # explicit __d*_rn intrinsics, which are never contracted.
 ]

@@ -489,7 +489,9 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     // frames k_front takes: long enough, and 16-byte aligned pairs (bulk copies, double2 reads)
     const bool base_ok = D.front && ((uintptr_t)d_samples & 15u) == 0;
     auto front_frame = [&](const FrameReq &r) {
-        return base_ok && r.len >= FRONT_MIN_SAMPLES && (r.len & 1u) == 0 && (r.off & 1ull) == 0;
+        // (the first Polynomial step of such a frame is 100 samples: N / max(3, N / 100), polynomial.rs:218-221)
+        return base_ok && r.len >= FRONT_MIN_SAMPLES && (r.len & 1u) == 0 && (r.off & 1ull) == 0 &&
+               r.len / std::max<uint32_t>(3, r.len / 100) == 100;
     };
     size_t n_chunks = 0, n_items = 0;
     for (uint32_t i = 0; i < n; i++) {

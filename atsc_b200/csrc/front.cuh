@@ -2,11 +2,12 @@
 //
 // The reference evaluates every candidate of a frame on one in-cache slice (frame/mod.rs:112-123).
 // Here a frame of >= FRONT_MIN_LEN samples is read from HBM ONCE: one CTA streams it through a
-// shared-memory ring filled by bulk asynchronous copies (cp.async.bulk + mbarrier, one elected
-// thread; SASS: UBLKCP / SYNCS) and, while a tile is on chip, computes
+// shared-memory ring filled by bulk asynchronous copies (cp.async.bulk + mbarrier, issued by a
+// producer warp; SASS: UBLKCP / SYNCS) and, while a tile is on chip, computes
 //   * DataStats + the run counts of IndexRLE      (optimizer/utils.rs:39-89, rle.rs:142-189),
 //   * the MAPE of the FIRST Polynomial candidate step, which is known before the stats are
-//     (step = N / max(3, N/100), polynomial.rs:209-277; utils/error.rs:104-116),
+//     (step = N / max(3, N/100) = 100 for every frame this kernel takes; polynomial.rs:209-277,
+//     utils/error.rs:104-116),
 //   * stage 1 of the FFT probe: the folds over the RA contiguous chunks of the padded frame
 //     (fft2.cuh: fold_acc) from which "at least c nonzero bins" is later proven without touching
 //     the samples again (fft.rs:249-252; pruning rule of frame/mod.rs:94-147).
@@ -20,6 +21,11 @@
 // values outside it are parked in a list and added, properly clamped, at the end of the frame.  A
 // frame that turns out not to be tame, overflows the list, or started with constant tiles whose
 // work was skipped falls back to k_poly / the old probe: same results, one more read.
+//
+// Ring: FR_SLOTS slots of [halo | tile].  A tile is 40 segments of the first step; the Polynomial
+// pass of a tile lags the stats pass by at most three segments (the tangent of a key needs the next
+// key), and those samples are copied into the NEXT slot's halo before the tile is released.  So only
+// the tile being worked on is pinned, three are in flight, and every address is linear.
 #pragma once
 #include "common.cuh"
 #include "fft2.cuh"
@@ -28,49 +34,51 @@
 
 namespace atsc {
 
-// -DFRONT_PROF: thread 0 of a few CTAs accumulates clock64() per phase and prints them at the end
-#ifdef FRONT_PROF
-#define FP_T(var) const long long var = clock64()
-#define FP_ADD(acc, t0) (acc) += clock64() - (t0)
-#else
-#define FP_T(var)
-#define FP_ADD(acc, t0)
-#endif
-struct FrontProf {
-    long long wait_full = 0, pass_a = 0, barrier = 0, pass_b = 0, tail = 0, head = 0, frames = 0, tiles = 0, trips = 0, ntrips = 0, parked = 0, syncw = 0, skew = 0, issue = 0, last15 = 0, last14 = 0, lastother = 0;
-};
-
-constexpr int FR_THREADS = 512;
-constexpr uint32_t FR_TILE = 4096;                     // samples per ring slot (32 KB)
-constexpr uint32_t FR_SLOTS = 4;                       // two tiles pinned (scan / polynomial), two in flight
-constexpr uint32_t FR_RING = FR_TILE * FR_SLOTS;       // samples; power of two
-constexpr uint32_t FR_MASK = FR_RING - 1;
-constexpr uint32_t FR_ROUNDS = FR_TILE / 2 / FR_THREADS;  // sample pairs per thread and tile
-constexpr uint32_t FR_FOLD_SLOTS = 18 * F2_M2;         // float4 (A, B) per slot m < RB*243
+constexpr int FR_THREADS = 512;                        // compute threads
+constexpr int FR_CTA = FR_THREADS + 32;                // + the producer warp
+constexpr uint32_t FR_PRODUCER = FR_THREADS;           // its first lane issues the bulk copies
+constexpr uint32_t FR_STEP = 100;                      // first Polynomial step of every frame k_front takes
+constexpr uint32_t FR_TILE = 40 * FR_STEP;             // samples per tile (32,000 B)
+constexpr uint32_t FR_HALO = 512;                      // samples kept from the previous tile (>= 3 segments)
+constexpr uint32_t FR_SLOT = FR_HALO + FR_TILE;        // samples per ring slot
+constexpr uint32_t FR_SLOTS = 4;
+constexpr uint32_t FR_ROUNDS = (FR_TILE / 2 + FR_THREADS - 1) / FR_THREADS;  // sample pairs per thread and tile
+constexpr uint32_t FR_G = FR_THREADS / FR_STEP;        // groups of FR_STEP threads (pass B)
 constexpr uint32_t FR_NS = 4;                          // adjacent segments per thread and trip (pass B)
-constexpr uint32_t FR_KMAX = 1320;                     // keys of a first step: N / 100 + 2 <= 1312
+constexpr uint32_t FR_TW = 512;                        // rolling window of keys / tangents
+constexpr uint32_t FR_FOLD_SLOTS = 18 * F2_M2;         // float4 (A, B) per slot m < RB*243
 constexpr uint32_t FR_LIST = 1024;                     // parked samples per frame
 constexpr uint32_t FRONT_MIN_LEN = 16384;
-constexpr uint32_t FR_PRODUCER = FR_THREADS;            // first lane of the extra warp that feeds the ring
-constexpr int FR_CTA = FR_THREADS + 32;                 // compute warps + the producer warp
-static_assert(FR_ROUNDS * 2 * FR_THREADS == FR_TILE, "tile = whole rounds of sample pairs");
+static_assert(FR_HALO >= 3 * FR_STEP + 4 && FR_HALO % 2 == 0, "halo covers the polynomial lag");
+static_assert((FR_SLOT * 8) % 16 == 0 && (FR_HALO * 8) % 16 == 0, "bulk copies are 16-byte aligned");
+
+// what the producer warp prepares for a frame while the previous one streams
+struct FrontDesc {
+    const double *d;   // the frame's samples in global memory
+    double first;      // sample 0
+    uint32_t idx;      // work item (>= n_items: none left)
+    uint32_t frame;    // index into the FrameWork table
+    uint32_t N, ntiles, mode;
+    uint32_t prefix, Cc, cmagic, RA;  // fold geometry (FM_FOLD)
+};
 
 struct FrontSmem {
-    double ring[FR_RING];
+    double ring[FR_SLOTS * FR_SLOT];
     float4 fold[FR_FOLD_SLOTS];
-    double tang[FR_KMAX];
+    double tang[FR_TW + 8];  // entries 0..7 mirrored behind the window: five consecutive reads never wrap
+    double keyv[FR_TW];
     uint32_t list[FR_LIST];
     double red[136];  // block reductions: 2 x 32 doubles + 4 x 32 words
     unsigned long long full[FR_SLOTS], empty[FR_SLOTS];
     unsigned long long pub_lo, pub_hi;  // ordered encodings of the range published so far
     float2 root[16];
+    FrontDesc desc[2];
     StatsPart part;
+    double s249, s250, lastv;      // samples captured while streaming
+    double fin_vmin, fin_vmax;     // the frame's final range, for the whole CTA
+    uint32_t fin_flags;            // bit0 need_poly (Catmull-Rom), bit1 need_fft, bits 8.. bitdepth
     uint32_t list_n;
     uint32_t varied[2];
-    int item;
-#ifdef FRONT_PROF
-    long long arr[32];
-#endif
 };
 constexpr int FRONT_SMEM_BYTES = (int)sizeof(FrontSmem);
 static_assert(sizeof(FrontSmem) <= 227 * 1024, "k_front shared memory");
@@ -82,13 +90,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(unsigned long long *b, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned long long *b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *b, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n"
@@ -97,20 +105,22 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *b, uint32_t pa
         "selp.u32 %0, 1, 0, p;\n"
         "}"
         : "=r"(ok)
-        : "r"(smem_u32(b)), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity) {
-    while (!mbar_try_wait(b, parity)) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
     }
 }
 // global -> shared bulk copy; dst, src and bytes are multiples of 16; completion counts on `bar`
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// the compute warps' barrier (the producer warp never joins it)
+__device__ __forceinline__ void front_bar() { asm volatile("bar.sync 1, %0;" ::"n"(FR_THREADS) : "memory"); }
 
 // order-preserving u64 encoding of a double (NaN never reaches it)
 __device__ __forceinline__ unsigned long long ord_enc(double x) {
@@ -121,23 +131,6 @@ __device__ __forceinline__ double ord_dec(unsigned long long e) {
     const unsigned long long b = (e >> 63) ? (e & 0x7FFFFFFFFFFFFFFFull) : ~e;
     return __longlong_as_double((long long)b);
 }
-
-// per-frame constants of the streaming pass
-struct FrontFrame {
-    const double *d;   // the frame's samples in global memory
-    uint32_t N, ntiles;
-    uint32_t rbase;    // ring index of sample 0
-    // polynomial first step
-    uint32_t step, K, Kreg, smagic;  // smagic: x / step == __umulhi(x, smagic) for x < 2^25
-    // fold
-    uint32_t prefix, Cc, cmagic, RA;
-};
-
-// the producer's view of a frame: what thread 0 needs to issue its tiles
-struct FrontFeed {
-    const double *d;
-    uint32_t N, ntiles, issued;  // tiles issued so far
-};
 
 // which candidates run for a frame whose stats are final (frame/mod.rs:71-149, compressor/mod.rs:63-107);
 // shared by k_plan and k_front
@@ -178,18 +171,23 @@ __device__ inline void plan_frame(FrameWork *fw) {
     fw->front_res = 0;
 }
 
+// per-frame constants of the compute threads
+struct FrontFrame {
+    uint32_t N, K, Kreg;
+    uint32_t prefix, Cc, cmagic;  // fold
+};
+
 // ---------------------------------------------------------------------------------------
-// pass A over samples [lo, hi) of tile `tile` (pointer to its first sample in the ring; lo, hi are
-// tile-local and even): stats + run ends (left-neighbour form: a sample that differs from its
-// predecessor ends a run at the predecessor's index) + the probe fold.  `pv_first`: the sample
-// before tile-local index 0 (the previous tile's last one; sample 0 itself for the frame's first tile).
+// pass A over samples [lo, hi) of a tile (tile-local, even): stats + run ends (left-neighbour form:
+// a sample that differs from its predecessor ends a run at the predecessor's index) + the probe
+// fold.  `pv0`: the sample before tile-local index 0 (only the thread of pair 0 uses it).
 // All loads of a thread's FR_ROUNDS pairs are issued before any of them is used.
 // BITS: the frame has been bit-constant so far; a warp whose samples all carry `first`'s bits skips
 // the stats arithmetic (every statistic is idempotent under a repeated value).
 // ---------------------------------------------------------------------------------------
 template <bool FOLD, bool BITS>
-__device__ __forceinline__ void front_scan(StatsAcc &a, FrontSmem *sm, const FrontFrame &f, const double *tile,
-                                           uint32_t x_tile, uint32_t lo, uint32_t hi, double pv_first, double first) {
+__device__ __forceinline__ void front_scan(StatsAcc &a, FrontSmem *sm, const FrontFrame &f, const double *tile, uint32_t x_tile,
+                                           uint32_t lo, uint32_t hi, double pv0, double first) {
     const uint32_t t = threadIdx.x;
     const uint32_t P = (hi - lo) >> 1;
     const double2 *tp = reinterpret_cast<const double2 *>(tile + lo);
@@ -200,7 +198,7 @@ __device__ __forceinline__ void front_scan(StatsAcc &a, FrontSmem *sm, const Fro
         const uint32_t p = t + r * FR_THREADS;
         if (p < P) {
             v[r] = tp[p];
-            pv[r] = (lo + 2u * p) ? tile[lo + 2u * p - 1u] : pv_first;
+            pv[r] = (lo + 2u * p) ? tile[lo + 2u * p - 1u] : pv0;
         } else {
             v[r] = make_double2(first, first);
             pv[r] = first;
@@ -253,35 +251,30 @@ __device__ __forceinline__ void front_scan(StatsAcc &a, FrontSmem *sm, const Fro
     }
 }
 
-// pass B, one block of G * FR_NS segments: thread (g, j) takes the FR_NS ADJACENT Catmull-Rom
-// segments s0 .. s0+3 at offset j (the inner keys and tangents are loaded once for the two segments
-// they bound); tame arithmetic, no clamp; values outside [lo, hi] are parked.
-template <bool LINEAR>
-__device__ __forceinline__ void front_poly_trip(FrontSmem *sm, const FrontFrame &f, uint32_t s0, uint32_t nseg, uint32_t base,
-                                                uint32_t j, double h00, double h10, double h01, double h11, double lo, double hi,
-                                                double &acc) {
-    const uint32_t step = f.step;
-    const double *ring = sm->ring;
-    double kv[FR_NS + 1], tv[FR_NS + 1], o[FR_NS], out[FR_NS], e[FR_NS];
-    const double *tg = sm->tang + s0;
-    if (LINEAR) {
-        const double *p = ring + base, *po = p + j;
-#pragma unroll
-        for (uint32_t u = 0; u <= FR_NS; u++) {
-            kv[u] = p[u * step];
-            tv[u] = tg[u];
-        }
-#pragma unroll
-        for (uint32_t u = 0; u < FR_NS; u++) o[u] = po[u * step];
+// values of the first step that the clamp cannot touch go into the sum; the others are parked
+__device__ __forceinline__ void front_take(FrontSmem *sm, double out, double e, double lo, double hi, uint32_t x, double &acc) {
+    if (out >= lo && out <= hi) {
+        acc += e;
     } else {
-#pragma unroll
-        for (uint32_t u = 0; u <= FR_NS; u++) {
-            kv[u] = ring[(base + u * step) & FR_MASK];
-            tv[u] = tg[u];
-        }
-#pragma unroll
-        for (uint32_t u = 0; u < FR_NS; u++) o[u] = ring[(base + u * step + j) & FR_MASK];
+        const uint32_t at = atomicAdd(&sm->list_n, 1u);
+        if (at < FR_LIST) sm->list[at] = x;
     }
+}
+
+// pass B, one trip: thread (g, j) takes the FR_NS ADJACENT Catmull-Rom segments s0 .. s0+3 at offset j
+// (the inner keys and tangents are loaded once for the two segments they bound); `p` points at key s0
+// in the ring (halo or tile: linear).  Tame arithmetic, no clamp.
+__device__ __forceinline__ void front_poly_trip(FrontSmem *sm, const double *p, uint32_t s0, uint32_t nseg, uint32_t j, double h00,
+                                                double h10, double h01, double h11, double lo, double hi, double &acc) {
+    double kv[FR_NS + 1], tv[FR_NS + 1], o[FR_NS], out[FR_NS], e[FR_NS];
+    const double *tg = sm->tang + (s0 & (FR_TW - 1u)), *po = p + j;
+#pragma unroll
+    for (uint32_t u = 0; u <= FR_NS; u++) {
+        kv[u] = p[u * FR_STEP];
+        tv[u] = tg[u];
+    }
+#pragma unroll
+    for (uint32_t u = 0; u < FR_NS; u++) o[u] = po[u * FR_STEP];
 #pragma unroll
     for (uint32_t u = 0; u < FR_NS; u++) {
         const double v = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(kv[u], h00), __dmul_rn(tv[u], h10)), __dmul_rn(kv[u + 1], h01)),
@@ -290,91 +283,96 @@ __device__ __forceinline__ void front_poly_trip(FrontSmem *sm, const FrontFrame 
         e[u] = mape_term_tame(out[u], o[u]);
     }
 #pragma unroll
-    for (uint32_t u = 0; u < FR_NS; u++) {
-        if (u < nseg) {
-            if (out[u] >= lo && out[u] <= hi) {
-                acc += e[u];
-            } else {
-                const uint32_t at = atomicAdd(&sm->list_n, 1u);
-                if (at < FR_LIST) sm->list[at] = (s0 + u) * step + j;
-            }
-        }
-    }
+    for (uint32_t u = 0; u < FR_NS; u++)
+        if (u < nseg) front_take(sm, out[u], e[u], lo, hi, (s0 + u) * FR_STEP + j, acc);
 }
 
-// producer thread: issues tile `feed.issued` of the frame described by `feed` into the next ring slot, as
-// FR_SPLIT bulk copies that complete on the slot's barrier (one copy in flight moves only a few GB/s;
-// the copy engine overlaps separate copies)
-constexpr uint32_t FR_SPLIT = 2;
-__device__ __forceinline__ void front_issue(FrontSmem *sm, FrontFeed &feed, uint32_t &fill) {
-    const uint32_t slot = fill % FR_SLOTS, k = feed.issued;
-    if (fill >= FR_SLOTS) mbar_wait(&sm->empty[slot], ((fill / FR_SLOTS) - 1u) & 1u);
-    const uint32_t cnt = min(FR_TILE, feed.N - k * FR_TILE);
-    mbar_expect_tx(&sm->full[slot], cnt * 8u);
-    constexpr uint32_t PART = FR_TILE / FR_SPLIT;  // samples per copy (even)
-    const double *src = feed.d + (size_t)k * FR_TILE;
-    double *dst = sm->ring + slot * FR_TILE;
-#pragma unroll
-    for (uint32_t c = 0; c < FR_SPLIT; c++) {
-        const uint32_t o = c * PART;
-        if (o < cnt) bulk_g2s(dst + o, src + o, min(PART, cnt - o) * 8u, &sm->full[slot]);
-    }
+// producer lane: issues tile `issued` of the frame described by `D` into the next ring slot.  It sits in
+// the highest-numbered warp, which the issue arbiter prefers: its wait backs off (`nap` ns) so that a hot
+// spin does not take issue slots from the compute warps of its sub-partition.
+__device__ __forceinline__ void front_issue(FrontSmem *sm, const FrontDesc &D, uint32_t &issued, uint32_t &fill, uint32_t full0,
+                                            uint32_t empty0, uint32_t nap) {
+    const uint32_t slot = fill % FR_SLOTS, k = issued;
+    if (fill >= FR_SLOTS)
+        while (!mbar_try_wait(empty0 + slot * 8u, ((fill / FR_SLOTS) - 1u) & 1u))
+            if (nap) __nanosleep(nap);
+    const uint32_t cnt = min(FR_TILE, D.N - k * FR_TILE);
+    mbar_expect_tx(full0 + slot * 8u, cnt * 8u);
+    bulk_g2s(sm->ring + slot * FR_SLOT + FR_HALO, D.d + (size_t)k * FR_TILE, cnt * 8u, full0 + slot * 8u);
     fill++;
-    feed.issued = k + 1u;
+    issued = k + 1u;
+}
+
+// producer lane: claims the next work item and describes its frame in *D
+__device__ inline void front_claim(FrontDesc *D, const FrameWork *fr, const uint32_t *__restrict__ items, uint32_t n_items,
+                                   const double *__restrict__ samples, const FftGeom *__restrict__ geoms, unsigned *q) {
+    const uint32_t idx = atomicAdd(q, 1u);
+    D->idx = idx;
+    D->N = D->ntiles = 0;
+    if (idx >= n_items) return;
+    const uint32_t fi = items[idx];
+    const FrameWork *fw = &fr[fi];
+    D->frame = fi;
+    D->d = samples + fw->off;
+    D->N = fw->len;
+    D->ntiles = (fw->len + FR_TILE - 1u) / FR_TILE;
+    D->mode = fw->front_mode;
+    D->prefix = D->Cc = D->cmagic = D->RA = 0;
+    if (fw->front_mode & FM_FOLD) {
+        const FftGeom *g = geoms + fw->geom;
+        D->RA = f2_fold_ra(g->M1);
+        D->Cc = (g->M1 / D->RA) * (uint32_t)F2_M2;
+        D->cmagic = (uint32_t)(0x100000000ull / D->Cc) + 1u;
+        D->prefix = (g->L - fw->len) / 2u;
+    }
+    D->first = __ldg(D->d);
 }
 
 // One frame through the ring.  All threads of the CTA call: FR_THREADS compute threads and the
 // producer warp, whose first lane (FR_PRODUCER) issues the bulk copies -- an issue costs that lane
 // about a thousand cycles, which would stall a whole compute warp at every barrier.  Compute warps
 // synchronise on named barrier 1 while they stream; the whole CTA meets again for the frame's tail.
-// fill / use: ring slots filled / consumed since the kernel started (`fill` is the producer's).
-// feed: the producer's state for THIS frame (its first tiles may already be in flight).  Having
-// issued this frame's last tile the producer claims the next work item (sm->item) and goes on with
-// that frame's tiles as slots come free, so the ring never drains between frames.
-__device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ items, uint32_t n_items, int item,
+// fill / use: ring slots filled / consumed since the kernel started (`fill`, `issued` are the
+// producer's).  Having issued this frame's last tile the producer claims the next work item
+// (sm->desc[(fc + 1) & 1]) and goes on with that frame's tiles as slots come free, so the ring
+// never drains between frames.
+__device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ items, uint32_t n_items, uint32_t fc,
                                    const double *__restrict__ samples, double max_err, const FftGeom *__restrict__ geoms,
                                    float4 *fold_arena, unsigned *q, FrontSmem *sm, uint32_t &fill, uint32_t &use,
-                                   FrontFeed &feed, FrontProf &prof, uint32_t dbg) {
+                                   uint32_t &issued, uint32_t nap) {
     const uint32_t t = threadIdx.x, lane = t & 31u;
-    FP_T(t_head);
     constexpr uint32_t T = FR_THREADS;
-    FrameWork *fw = &fr[items[item]];
+    const bool compute = t < T;
+    const FrontDesc &D = sm->desc[fc & 1u];
+    FrameWork *fw = &fr[D.frame];
+    const double *d = D.d;
     FrontFrame f;
-    f.N = fw->len;
-    f.d = samples + fw->off;
-    f.ntiles = (f.N + FR_TILE - 1u) / FR_TILE;
-    f.rbase = (use % FR_SLOTS) * FR_TILE;
-    const uint8_t mode = fw->front_mode;
+    f.N = D.N;
+    const uint32_t ntiles = D.ntiles;
+    const uint8_t mode = (uint8_t)D.mode;
     const bool do_poly = (mode & FM_POLY) != 0;
     const bool do_fold = (mode & FM_FOLD) != 0;
-    const uint32_t baseline = (3u >= f.N / 100u) ? 3u : f.N / 100u;
-    f.step = max(f.N / baseline, 1u);
-    f.smagic = (uint32_t)(0x100000000ull / f.step) + 1u;
     {
-        const PolyKeys k = poly_keys(f.N, f.step);
+        const PolyKeys k = poly_keys(f.N, FR_STEP);
         f.K = k.K;
         f.Kreg = k.Kreg;
     }
-    f.prefix = f.Cc = f.cmagic = f.RA = 0;
-    if (do_fold) {
-        const FftGeom *g = geoms + fw->geom;
-        f.RA = f2_fold_ra(g->M1);
-        f.Cc = (g->M1 / f.RA) * (uint32_t)F2_M2;
-        f.cmagic = (uint32_t)(0x100000000ull / f.Cc) + 1u;
-        f.prefix = (g->L - f.N) / 2u;
-    }
-    const bool compute = t < T;
+    f.prefix = D.prefix;
+    f.Cc = D.Cc;
+    f.cmagic = D.cmagic;
+    const uint32_t RA = D.RA;
+    const double first = D.first;
+    const uint32_t full0 = smem_u32(&sm->full[0]), empty0 = smem_u32(&sm->empty[0]);
     if (t == 0) {
         sm->list_n = 0;
         sm->varied[0] = sm->varied[1] = 0;
         sm->pub_lo = ord_enc(__longlong_as_double(0x7FF0000000000000ll));
         sm->pub_hi = ord_enc(__longlong_as_double((long long)0xFFF0000000000000ull));
     }
-    const double first = __ldg(f.d);
-    if (do_fold) {
+    if (do_fold && compute) {
         if (t < 16u) {
             float2 r = make_float2(1.f, 0.f);
-            switch (f.RA) {
+            switch (RA) {
                 case 16: r = root_c<16, false>((int)t); break;
                 case 8: r = root_c<8, false>((int)(t & 7u)); break;
                 default: r = root_c<4, false>((int)(t & 3u)); break;
@@ -385,16 +383,14 @@ __device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ i
         float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f);
         fold_acc(p0, (float)first, (float)first, make_float2(1.f, 0.f));
         const uint32_t np = f.prefix >> 1;
-        if (compute)
-            for (uint32_t m = t; m < f.Cc; m += T) sm->fold[m] = m < np ? p0 : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t m = t; m < f.Cc; m += T) sm->fold[m] = m < np ? p0 : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     // Hermite basis of this thread's offset inside the segments (poly.cuh: poly_mape)
-    const uint32_t G = T / f.step, g = t / f.step, j = t - g * f.step;
-    const uint32_t BS = G * FR_NS;  // segments per block
-    const double stepd = (double)f.step;
-    double h00 = 0.0, h10 = 0.0, h01 = 0.0, h11 = 0.0;
-    if (do_poly && g < G) {
-        const double tt = __ddiv_rn((double)j, stepd);
+    const uint32_t g = t / FR_STEP, j = t - g * FR_STEP;
+    constexpr double stepd = (double)FR_STEP;
+    double tt = 0.0, h00 = 0.0, h10 = 0.0, h01 = 0.0, h11 = 0.0;
+    if (do_poly && g < FR_G) {
+        tt = __ddiv_rn((double)j, stepd);
         const double two_t = __dmul_rn(tt, 2.0), three_t = __dmul_rn(tt, 3.0);
         const double t2 = __dmul_rn(tt, tt), t3 = __dmul_rn(t2, tt);
         const double two_t3 = __dmul_rn(t2, two_t), two_t2 = __dmul_rn(tt, two_t), three_t2 = __dmul_rn(tt, three_t);
@@ -417,92 +413,56 @@ __device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ i
     double acc = 0.0;
     bool seen_var = !(first == first);  // a NaN first sample: min = max = NaN, never "constant"
     bool skipped = false;
-    // pass-B bookkeeping, advanced block by block without divisions: the block's first segment for this
-    // thread, its ring index, and the position of the key that must have landed before the block runs
     const uint32_t s_last = f.K >= 4u ? f.K - 3u : 0u;  // last Catmull-Rom segment (0: none)
-    const uint32_t blk_span = BS * f.step;
-    uint32_t sb = 1u;                                   // first segment of the next block
-    uint32_t s0 = 1u + FR_NS * g;                       // ... and of this thread's trip in it
-    uint32_t base = (s0 * f.step + f.rbase) & FR_MASK;
-    uint32_t need_pos = (BS + 2u) * f.step;             // key (b+1)*BS + 2: its tangent neighbour closes the block
-    uint32_t kk_next = 0;                               // next key whose arrival the tangent pass handles
-    const uint32_t full0 = smem_u32(&sm->full[0]), empty0 = smem_u32(&sm->empty[0]);
+    uint32_t s_next = 1u;                               // first Catmull-Rom segment not yet evaluated
+    double prev_last = first;                           // thread 0: the sample before the current tile
     __syncthreads();  // fold / list / flags initialised
-    FP_ADD(prof.head, t_head);
 
-    // Two phases per iteration: pass A of the tile that lands now (with the tangents of the keys it
-    // brings), a barrier, then pass B of every block that is complete with it.  Two tiles are pinned
-    // (i-1: pass B still reads it; i), the other two ring slots are in flight.
     if (!compute) {
         // ---- producer warp: this frame's tiles, then the next frame's first ones, paced by the empty barriers
         if (t == FR_PRODUCER) {
-            while (feed.issued < f.ntiles) front_issue(sm, feed, fill);
-            const int nxt = (int)atomicAdd(q, 1u);
-            sm->item = nxt;
-            feed.issued = 0;
-            feed.N = 0;
-            feed.ntiles = 0;
-            if (nxt < (int)n_items) {
-                const FrameWork *nf = &fr[items[nxt]];
-                feed.d = samples + nf->off;
-                feed.N = nf->len;
-                feed.ntiles = (feed.N + FR_TILE - 1u) / FR_TILE;
-                // slots still in use by this frame are waited for: the producer runs as far ahead as the ring allows
-                while (feed.issued < min(feed.ntiles, FR_SLOTS)) front_issue(sm, feed, fill);
-            }
+            while (issued < ntiles) front_issue(sm, D, issued, fill, full0, empty0, nap);
+            FrontDesc *nd = &sm->desc[(fc + 1u) & 1u];
+            front_claim(nd, fr, items, n_items, samples, geoms, q);
+            issued = 0;
+            while (issued < min(nd->ntiles, FR_SLOTS)) front_issue(sm, *nd, issued, fill, full0, empty0, nap);
         }
         __syncwarp();
-    } else
-    for (uint32_t i = 0; i <= f.ntiles; i++) {
-        const bool drain = i == f.ntiles;
-        uint32_t frontier = f.N;
-        if (!drain) {
+    } else {
+        for (uint32_t i = 0; i < ntiles; i++) {
             const uint32_t u = use + i, slot = u % FR_SLOTS;
-            FP_T(t_w);
-            {
-                const uint32_t bar = full0 + slot * 8u, par = (u / FR_SLOTS) & 1u;
-                uint32_t ok;
-                do {
-                    asm volatile(
-                        "{\n"
-                        ".reg .pred p;\n"
-                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-                        "selp.u32 %0, 1, 0, p;\n"
-                        "}"
-                        : "=r"(ok)
-                        : "r"(bar), "r"(par)
-                        : "memory");
-                } while (!ok);
-            }
-            FP_ADD(prof.wait_full, t_w);
-            FP_T(t_a);
             const uint32_t xa = i * FR_TILE, xb = min(xa + FR_TILE, f.N);
-            frontier = xb;
-            const double *tile = sm->ring + slot * FR_TILE;
-            const double pv_first = i ? sm->ring[(slot * FR_TILE - 1u) & FR_MASK] : first;
-            const bool fold_now = do_fold && (seen_var || i == 0) && !(dbg & 2u);
+            const double *tile = sm->ring + slot * FR_SLOT + FR_HALO;
+            mbar_wait(full0 + slot * 8u, (u / FR_SLOTS) & 1u);
+            // ---- pass A: stats, run ends by index class [0, 250) | [250, 65536) | [65536, ..), fold
+            const bool fold_now = do_fold && (seen_var || i == 0);
             if (do_fold && !fold_now) skipped = true;
-            // index classes of the run ends: [0, 250) | [250, 65536) | [65536, ..): 250 splits tile 0 only
-            const uint32_t e0 = a.ends;
-            auto scan = [&](uint32_t lo, uint32_t hi) {
-                if (dbg & 1u) {
-                    a.negz &= (uint32_t)__double2loint(tile[lo + 2u * t]);  // timing experiments only: touch the tile
-                } else if (seen_var) {
-                    if (fold_now) front_scan<true, false>(a, sm, f, tile, xa, lo, hi, pv_first, first);
-                    else front_scan<false, false>(a, sm, f, tile, xa, lo, hi, pv_first, first);
+            auto scan = [&](uint32_t lo, uint32_t hi) {  // frame indices, even
+                if (lo >= hi) return;
+                if (seen_var) {
+                    if (fold_now) front_scan<true, false>(a, sm, f, tile, xa, lo - xa, hi - xa, prev_last, first);
+                    else front_scan<false, false>(a, sm, f, tile, xa, lo - xa, hi - xa, prev_last, first);
                 } else {
-                    if (fold_now) front_scan<true, true>(a, sm, f, tile, xa, lo, hi, pv_first, first);
-                    else front_scan<false, true>(a, sm, f, tile, xa, lo, hi, pv_first, first);
+                    if (fold_now) front_scan<true, true>(a, sm, f, tile, xa, lo - xa, hi - xa, prev_last, first);
+                    else front_scan<false, true>(a, sm, f, tile, xa, lo - xa, hi - xa, prev_last, first);
                 }
             };
-            if (xa == 0) {
-                const uint32_t mid = min(250u, xb);
-                scan(0, mid);
-                const uint32_t e1 = a.ends;
-                if (mid < xb) scan(mid, xb);
-                ends250 += a.ends - e1;
+            if (xa < 250u || (xa < 65536u && xb > 65536u)) {  // a class boundary inside the tile (tile 0; one more tile)
+                scan(xa, min(xb, 250u));
+                uint32_t e0 = a.ends;
+                scan(max(xa, 250u), min(xb, 65536u));
+                ends250 += a.ends - e0;
+                e0 = a.ends;
+                scan(max(xa, 65536u), xb);
+                ends250 += a.ends - e0;
+                ends64k += a.ends - e0;
+                if (xa == 0 && t == 1u && xb > 250u) {
+                    sm->s249 = tile[249];
+                    sm->s250 = tile[250];
+                }
             } else {
-                scan(0, xb - xa);
+                const uint32_t e0 = a.ends;
+                scan(xa, xb);
                 ends250 += a.ends - e0;
                 if (xa >= 65536u) ends64k += a.ends - e0;
             }
@@ -522,83 +482,86 @@ __device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ i
                 }
                 if (!seen_var && (mn < first || mx > first)) sm->varied[i & 1u] = 1u;
             }
-            // tangents of the keys whose right-hand neighbour key landed with this tile
+            // keys of this tile and the tangents they complete: tangent kk-1 = (key kk - key kk-2) / 200 * 100
             if (do_poly) {
-                const uint32_t kk_hi = min(__umulhi(xb - 1u, f.smagic), f.Kreg - 1u);  // last regular key in the tile
-                const uint32_t kk = kk_next + (FR_THREADS - 1u - t);  // the last warps have idle lanes in pass B
-                if (kk <= kk_hi && kk >= 2u && kk + 1u <= f.K) {  // tangent index kk - 1 in [1, K - 2]
-                    const uint32_t pa = (kk - 2u) * f.step, pb = kk * f.step;
-                    const double va = sm->ring[(pa + f.rbase) & FR_MASK], vb = sm->ring[(pb + f.rbase) & FR_MASK];
-                    sm->tang[kk - 1u] = __dmul_rn(__ddiv_rn(__dsub_rn(vb, va), __dsub_rn((double)pb, (double)pa)), stepd);
-                }
-                kk_next = kk_hi + 1u;
-                if (xb == f.N && f.K == f.Kreg + 1u && f.K >= 3u && t == 64u) {  // the appended last key N - 1
-                    const uint32_t jt = f.K - 2u, pa = (jt - 1u) * f.step, pb = f.N - 1u;
-                    const double va = sm->ring[(pa + f.rbase) & FR_MASK], vb = sm->ring[(pb + f.rbase) & FR_MASK];
-                    sm->tang[jt] = __dmul_rn(__ddiv_rn(__dsub_rn(vb, va), __dsub_rn((double)pb, (double)pa)), stepd);
-                }
-            }
-            FP_ADD(prof.pass_a, t_a);
-        }
-        FP_T(t_bar);
-#ifdef FRONT_PROF
-        if (lane == 0) sm->arr[t >> 5] = clock64();
-#endif
-        asm volatile("bar.sync 1, %0;" ::"n"(FR_THREADS) : "memory");  // compute warps only
-#ifdef FRONT_PROF
-        if (t == 0) {
-            long long mn = sm->arr[0], mx = sm->arr[0];
-            int who = 0;
-            for (int k = 1; k < (int)(T >> 5); k++) {
-                if (sm->arr[k] < mn) mn = sm->arr[k];
-                if (sm->arr[k] > mx) { mx = sm->arr[k]; who = k; }
-            }
-            prof.skew += mx - mn;
-            if (who == 15) prof.last15++; else if (who == 14) prof.last14++; else prof.lastother++;
-        }
-#endif
-        FP_ADD(prof.barrier, t_bar);
-        FP_T(t_b);
-        if (!drain && !seen_var) seen_var = sm->varied[i & 1u] != 0u;
-        // ---- pass B: every block whose last tangent exists (key (b+1)*BS + 2 landed), all at the drain
-        if (do_poly && s_last) {
-            if (sb <= s_last && (drain || need_pos < frontier)) {
-                const double lo = ord_dec(sm->pub_lo), hi = ord_dec(sm->pub_hi);
-                do {
-                    if (!seen_var || (dbg & 4u)) {
-                        skipped = true;
-                    } else if (g < G && s0 <= s_last) {
-                        const uint32_t nseg = min(FR_NS, s_last + 1u - s0);
-                        FP_T(t_tr);
-                        if (base + (FR_NS + 1u) * f.step < FR_RING)
-                            front_poly_trip<true>(sm, f, s0, nseg, base, j, h00, h10, h01, h11, lo, hi, acc);
-                        else
-                            front_poly_trip<false>(sm, f, s0, nseg, base, j, h00, h10, h01, h11, lo, hi, acc);
-                        FP_ADD(prof.trips, t_tr);
-                        prof.ntrips += 1;
+                const uint32_t kk_lo = (xa + FR_STEP - 1u) / FR_STEP, kk_hi = min((xb - 1u) / FR_STEP, f.Kreg - 1u);
+                const uint32_t kk = kk_lo + (T - 1u - t);  // the last warps have idle lanes in pass B
+                if (kk <= kk_hi) {
+                    const double vk = tile[kk * FR_STEP - xa];
+                    sm->keyv[kk & (FR_TW - 1u)] = vk;
+                    if (kk >= 2u && kk + 1u <= f.K) {  // tangent index kk - 1 in [1, K - 2]
+                        const uint32_t pa = (kk - 2u) * FR_STEP;
+                        const double va = pa >= xa ? tile[pa - xa] : sm->keyv[(kk - 2u) & (FR_TW - 1u)];
+                        const double tg = __dmul_rn(__ddiv_rn(__dsub_rn(vk, va), 2.0 * stepd), stepd);
+                        const uint32_t ti = (kk - 1u) & (FR_TW - 1u);
+                        sm->tang[ti] = tg;
+                        if (ti < 8u) sm->tang[ti + FR_TW] = tg;
                     }
-                    sb += BS;
-                    s0 += BS;
-                    base = (base + blk_span) & FR_MASK;
-                    need_pos += blk_span;
-                } while (sb <= s_last && (drain || need_pos < frontier));
+                }
+                if (xb == f.N && f.K == f.Kreg + 1u && t == 64u) {  // the appended last key N - 1 closes tangent K - 2
+                    const uint32_t jt = f.K - 2u, pa = (jt - 1u) * FR_STEP, pb = f.N - 1u;
+                    const double va = pa >= xa ? tile[pa - xa] : sm->keyv[(jt - 1u) & (FR_TW - 1u)], vb = tile[pb - xa];
+                    const double tg = __dmul_rn(__ddiv_rn(__dsub_rn(vb, va), __dsub_rn((double)pb, (double)pa)), stepd);
+                    const uint32_t ti = jt & (FR_TW - 1u);
+                    sm->tang[ti] = tg;
+                    if (ti < 8u) sm->tang[ti + FR_TW] = tg;
+                }
             }
-        }
-        // release tile i-1: the unfinished blocks start within 22 * step of the frontier, inside tile i
-        if (i >= 1u) {
-            FP_T(t_sw);
+            front_bar();
+            if (!seen_var) seen_var = sm->varied[i & 1u] != 0u;
+            // ---- pass B: the Catmull-Rom segments whose right-hand tangent exists (key s + 2 landed)
+            if (do_poly && s_last) {
+                const uint32_t s_max = xb == f.N ? s_last : min(s_last, (xb - 1u) / FR_STEP - 2u);
+                const double lo = ord_dec(sm->pub_lo), hi = ord_dec(sm->pub_hi);
+                if (!seen_var) {
+                    skipped = true;
+                } else {
+                    if (g < FR_G) {
+                        const double *p0 = tile + (int)(s_next * FR_STEP) - (int)xa;  // key s_next: in the halo for the first segments
+                        for (uint32_t s0 = s_next + FR_NS * g; s0 <= s_max; s0 += FR_NS * FR_G)
+                            front_poly_trip(sm, p0 + (s0 - s_next) * FR_STEP, s0, min(FR_NS, s_max + 1u - s0), j, h00, h10, h01, h11,
+                                            lo, hi, acc);
+                    }
+                    // the Linear ends (polynomial.rs:349): segment 0 with the first tile, segment K-2 and the
+                    // last sample with the last one -- same parking rule
+                    if (i == 0 && g == 0) {
+                        const double v = __dadd_rn(__dmul_rn(tile[0], __dsub_rn(1.0, tt)), __dmul_rn(tile[FR_STEP], tt));
+                        const double out = div_1e5_int53(round_half_away(__dmul_rn(v, 100000.0)));
+                        front_take(sm, out, mape_term_tame(out, tile[j]), lo, hi, j, acc);
+                    }
+                    if (xb == f.N) {
+                        const uint32_t start_last = (f.K - 2u) * FR_STEP, x = start_last + (T - 1u - t);
+                        if (x < f.N) {
+                            double v = tile[f.N - 1u - xa];
+                            if (x != f.N - 1u) {
+                                const double at = (double)start_last, bt = (double)(f.N - 1u);
+                                const double nt = __ddiv_rn(__dsub_rn((double)x, at), __dsub_rn(bt, at));
+                                const double ka = tile[(int)start_last - (int)xa];
+                                v = __dadd_rn(__dmul_rn(ka, __dsub_rn(1.0, nt)), __dmul_rn(v, nt));
+                            }
+                            const double out = div_1e5_int53(round_half_away(__dmul_rn(v, 100000.0)));
+                            front_take(sm, out, mape_term_tame(out, tile[(int)x - (int)xa]), lo, hi, x, acc);
+                        }
+                    }
+                }
+                s_next = s_max + 1u;
+            }
+            // ---- the next tile's halo, the carry of thread 0, release
+            if (xb < f.N) {
+                if (t < FR_HALO / 2u) {
+                    const double2 hv = *reinterpret_cast<const double2 *>(tile + FR_TILE - FR_HALO + 2u * t);
+                    *reinterpret_cast<double2 *>(sm->ring + ((u + 1u) % FR_SLOTS) * FR_SLOT + 2u * t) = hv;
+                }
+            } else if (t == 0) {
+                sm->lastv = tile[f.N - 1u - xa];
+            }
+            if (t == 0) prev_last = tile[xb - xa - 1u];
             __syncwarp();
-            if (lane == 0)
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + ((use + i - 1u) % FR_SLOTS) * 8u) : "memory");
-            FP_ADD(prof.syncw, t_sw);
+            if (lane == 0) mbar_arrive(empty0 + slot * 8u);
         }
-        FP_ADD(prof.pass_b, t_b);
     }
-    FP_T(t_tail);
-    prof.parked += sm->list_n;
-    prof.frames += 1;
-    prof.tiles += f.ntiles;
-    use += f.ntiles;
+    use += ntiles;
+
     // ======================= end of the frame: stats =======================
     {
         if (a.negz == 0u) a.flags |= 2u;
@@ -640,7 +603,7 @@ __device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ i
                 r2 += ru[96 + k];
             }
             // the end at index 249 was counted with the [250, ..) class (left-neighbour form)
-            if (f.N > 250u && f.d[250] != f.d[249]) r1 -= 1u;
+            if (f.N > 250u && sm->s250 != sm->s249) r1 -= 1u;
             StatsPart p;
             p.mn = mn;
             p.mx = mx;
@@ -649,16 +612,20 @@ __device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ i
             p.ends251 = r1;
             p.ends64k = r2;
             sm->part = p;
-            finish_stats(f.d, f.N, &sm->part, 1, fw);
+            finish_stats_with(first, d, f.N, &sm->part, 1, fw);
             plan_frame(fw);
             if (skipped && seen_var) fw->front_mode = mode & ~FM_FOLD;  // the fold misses tiles: old probe
+            sm->fin_vmin = fw->vmin;
+            sm->fin_vmax = fw->vmax;
+            sm->fin_flags = ((fw->need_poly && fw->poly_type == 0) ? 1u : 0u) | (fw->need_fft ? 2u : 0u) | ((uint32_t)fw->bitdepth << 8);
         }
         __syncthreads();
     }
     // ======================= first Polynomial step =======================
-    const double vmin = fw->vmin, vmax = fw->vmax;
-    if (do_poly && fw->need_poly && fw->poly_type == 0) {
-        const PolyKeys k = poly_keys(f.N, f.step);
+    const double vmin = sm->fin_vmin, vmax = sm->fin_vmax;
+    const uint32_t fin = sm->fin_flags;
+    if (do_poly && (fin & 1u)) {
+        const PolyKeys k = poly_keys(f.N, FR_STEP);
         if (vmax == vmin) {
             // polynomial.rs:210,280 "Same max and min": no points
             if (t == 0) {
@@ -670,23 +637,22 @@ __device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ i
                 fw->poly_err = 0.0;
                 fw->poly_valid = 1;
             }
-        } else if (!skipped && poly_tame(vmin, vmax) && sm->list_n <= FR_LIST && f.K >= 4u && f.step < (uint32_t)POLY_MAXSTEP) {
+        } else if (!skipped && poly_tame(vmin, vmax) && sm->list_n <= FR_LIST && f.K >= 4u) {
             // parked samples: the generic arithmetic with the frame's final clamp
-            auto pts = [&](uint32_t qk) { return f.d[poly_pos(k, qk)]; };
+            auto pts = [&](uint32_t qk) { return d[poly_pos(k, qk)]; };
             const uint32_t nl = sm->list_n;
             for (uint32_t c = t; c < nl; c += FR_CTA) {
                 const uint32_t x = sm->list[c];
-                acc += mape_term(round_and_limit5_fast(poly_eval_at(k, x, pts), vmin, vmax), f.d[x]);
+                acc += mape_term(round_and_limit5_fast(poly_eval_at(k, x, pts), vmin, vmax), d[x]);
             }
-            acc += poly_mape_ends(f.d, k, vmin, vmax);
             const double s = block_sum(acc, sm->red);
             const double cur = __ddiv_rn(s, (double)f.N);
             const double target = round_f64_dec(max_err, 3);
             const bool pass = !(target < round_f64_dec(cur, 4));  // polynomial.rs:231: the loop ends here
             uint32_t size = 0;
-            if (pass) size = poly_payload_size(f.d, k, fw->bitdepth, false, reinterpret_cast<uint32_t *>(sm->red));
+            if (pass) size = poly_payload_size(d, k, (int)(fin >> 8), false, reinterpret_cast<uint32_t *>(sm->red));
             if (t == 0) {
-                fw->poly_step = f.step;
+                fw->poly_step = FR_STEP;
                 fw->poly_err = cur;
                 if (pass) {
                     fw->poly_npts = k.K;
@@ -701,23 +667,19 @@ __device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ i
         }
     }
     // ======================= fold -> arena =======================
-    if (do_fold && !(skipped && seen_var) && fw->need_fft) {
-        __syncthreads();
+    if (do_fold && !(skipped && seen_var) && (fin & 2u)) {
         // the gibbs suffix replicates the last sample: the last chunk of the slots from (prefix + N) / 2 on
-        const float lastf = (float)f.d[f.N - 1u];
-        const float2 w = sm->root[f.RA - 1u];
-        const uint32_t m0 = ((f.prefix + f.N) >> 1) - (f.RA - 1u) * f.Cc;
-        for (uint32_t m = m0 + t; m < f.Cc; m += FR_CTA) {
-            float4 ab = sm->fold[m];
-            fold_acc(ab, lastf, lastf, w);
-            sm->fold[m] = ab;
-        }
-        __syncthreads();
+        const float lastf = (float)sm->lastv;
+        const float2 w = sm->root[RA - 1u];
+        const uint32_t m0 = ((f.prefix + f.N) >> 1) - (RA - 1u) * f.Cc;
         float4 *dst = fold_arena + (size_t)fw->fold_idx * FR_FOLD_SLOTS;
-        for (uint32_t m = t; m < f.Cc; m += FR_CTA) __stcg(dst + m, sm->fold[m]);
+        for (uint32_t m = t; m < f.Cc; m += FR_CTA) {
+            float4 ab = sm->fold[m];
+            if (m >= m0) fold_acc(ab, lastf, lastf, w);
+            __stcg(dst + m, ab);
+        }
     }
     __syncthreads();
-    FP_ADD(prof.tail, t_tail);
 }
 
 }  // namespace atsc

@@ -6,8 +6,8 @@
 // Reference citations are relative to /root/reference/atsc/src/.
 #include "kernels.h"
 
-#include <cstdio>
 #include <cstdlib>
+
 #include "fft2.cuh"
 #include "fft_small.cuh"
 #include "front.cuh"
@@ -72,43 +72,25 @@ __global__ void k_plan(FrameWork *fr, uint32_t n, const double *__restrict__ sam
 // Fused front end of the big frames (front.cuh): stats + first Polynomial step + FFT probe fold in
 // ONE pass over the samples, staged through shared memory by bulk asynchronous copies.
 __global__ void __launch_bounds__(FR_CTA, 1) k_front(FrameWork *fr, const uint32_t *__restrict__ items, uint32_t n_items,
-                                                        const double *__restrict__ samples, double max_err,
-                                                        const FftGeom *__restrict__ geoms, float4 *fold_arena, unsigned *q, uint32_t dbg) {
+                                                     const double *__restrict__ samples, double max_err,
+                                                     const FftGeom *__restrict__ geoms, float4 *fold_arena, unsigned *q,
+                                                     uint32_t nap) {
     extern __shared__ __align__(128) unsigned char dyn_front[];
     FrontSmem *sm = reinterpret_cast<FrontSmem *>(dyn_front);
-    uint32_t fill = 0, use = 0;
-    FrontFeed feed;
-    feed.d = samples;
-    feed.N = feed.ntiles = feed.issued = 0;
+    uint32_t fill = 0, use = 0, issued = 0;
     if (threadIdx.x == FR_PRODUCER) {
         for (uint32_t s = 0; s < FR_SLOTS; s++) {
             mbar_init(&sm->full[s], 1u);
             mbar_init(&sm->empty[s], FR_THREADS / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const int first = (int)atomicAdd(q, 1u);
-        sm->item = first;
-        if (first < (int)n_items) {
-            const FrameWork *nf = &fr[items[first]];
-            feed.d = samples + nf->off;
-            feed.N = nf->len;
-            feed.ntiles = (feed.N + FR_TILE - 1u) / FR_TILE;
-        }
+        front_claim(&sm->desc[0], fr, items, n_items, samples, geoms, q);
     }
     __syncthreads();
-    FrontProf prof;
-    for (;;) {
-        const int it = sm->item;  // the producer claims the next item while a frame's tail runs (front_frame)
-        if (it >= (int)n_items) break;
-        front_frame(fr, items, n_items, it, samples, max_err, geoms, fold_arena, q, sm, fill, use, feed, prof, dbg);
+    for (uint32_t fc = 0;; fc++) {
+        if (sm->desc[fc & 1u].idx >= n_items) break;  // the producer claims the next item while a frame streams
+        front_frame(fr, items, n_items, fc, samples, max_err, geoms, fold_arena, q, sm, fill, use, issued, nap);
     }
-#ifdef FRONT_PROF
-    if (threadIdx.x == FR_PRODUCER && blockIdx.x == 77) printf("k_front cta 77 producer: issue cycles %lld\n", prof.issue);
-    if (threadIdx.x == 0 && blockIdx.x == 77) printf("k_front cta 77: arrival skew (max - min) total %lld; last warp 15: %lld, 14: %lld, other: %lld\n", prof.skew, prof.last15, prof.last14, prof.lastother);
-    if ((threadIdx.x == 0 || threadIdx.x == 288) && (blockIdx.x == 0 || blockIdx.x == 77))
-        printf("k_front cta %d thr %d: frames %lld tiles %lld | cycles head %lld wait_full %lld pass_a %lld barrier %lld pass_b %lld (trips %lld x %lld, syncwarp %lld) tail %lld | parked %lld\n",
-               blockIdx.x, threadIdx.x, prof.frames, prof.tiles, prof.head, prof.wait_full, prof.pass_a, prof.barrier, prof.pass_b, prof.ntrips, prof.ntrips ? prof.trips / prof.ntrips : 0, prof.syncw, prof.tail, prof.parked);
-#endif
 }
 
 // =========================================================================================
@@ -1177,9 +1159,10 @@ void launch_fft_fwd(FrameWork *fr, uint32_t n, const double *samples, double max
 }
 void launch_front(FrameWork *fr, const uint32_t *items, uint32_t n_items, const double *samples, double max_err,
                   const FftGeom *geoms, float4 *fold_arena, unsigned *q, cudaStream_t st) {
-    static const uint32_t dbg = getenv("ATSC_FRONT_DBG") ? (uint32_t)atoi(getenv("ATSC_FRONT_DBG")) : 0u;  // timing experiments
+    // back-off (ns) of the producer lane's wait for a free ring slot (tunable for experiments)
+    static const uint32_t nap = getenv("ATSC_FRONT_NAP") ? (uint32_t)atoi(getenv("ATSC_FRONT_NAP")) : 64u;
     k_front<<<grid_for(n_items, sms()), FR_CTA, FRONT_SMEM_BYTES, st>>>(fr, items, n_items, samples, max_err, geoms,
-                                                                            fold_arena, q, dbg);
+                                                                        fold_arena, q, nap);
 }
 void launch_noop_size(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st) {
     k_noop_size<<<grid_for(n, 2 * sms()), BLOCK, 0, st>>>(fr, n, samples, q);

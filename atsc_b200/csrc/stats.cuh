@@ -211,9 +211,8 @@ __device__ inline void chunk_stats(const double *__restrict__ d, uint32_t N, uin
 // data[0], strict comparisons in index order (NaN never wins).  Equal values have equal bits except
 // +0.0 / -0.0, so "first occurrence" only matters when an extreme is zero and a -0.0 exists: that
 // (rare) case scans for the first zero.
-__device__ inline void finish_stats(const double *__restrict__ d, uint32_t N, const StatsPart *parts, uint32_t nparts,
-                                    FrameWork *fw) {
-    const double first = d[0];
+__device__ inline void finish_stats_with(double first, const double *__restrict__ d, uint32_t N, const StatsPart *parts,
+                                         uint32_t nparts, FrameWork *fw) {
     double mn = first, mx = first;
     uint32_t flags = 0, runs = 1, idxb = 0;  // runs: + the run that ends with the last sample
     for (uint32_t k = 0; k < nparts; k++) {
@@ -258,6 +257,10 @@ __device__ inline void finish_stats(const double *__restrict__ d, uint32_t N, co
     fw->f32_const = ((float)vmax == (float)vmin) ? 1 : 0;
     fw->n_runs = runs;
     fw->rle_idx_bytes = idxb + 1;  // + varint_len(0) for the first run
+}
+__device__ inline void finish_stats(const double *__restrict__ d, uint32_t N, const StatsPart *parts, uint32_t nparts,
+                                    FrameWork *fw) {
+    finish_stats_with(d[0], d, N, parts, nparts, fw);
 }
 
 }  // namespace atsc
