@@ -72,8 +72,6 @@ struct Engine {
     size_t arena_cap = 0;
     uint32_t *d_items = nullptr, *h_items = nullptr;  // frames of the wave that go through k_front
     size_t items_cap = 0;
-    float4 *d_fold = nullptr;  // probe folds of the wave (k_front -> k_fft_fwd)
-    size_t fold_cap = 0;
     float2 *d_spec_xd = nullptr;  // per-frame half spectra of the wave (k_fft_fwd -> k_fft)
     uint32_t *d_spec_keys = nullptr;
     size_t spec_xd_cap = 0, spec_keys_cap = 0;
@@ -99,7 +97,11 @@ struct Device {
     int id = 0;
     cudaStream_t st = nullptr;  // setup stream (tables)
     int n_engines = 0, sms = 0;
-    bool front = true;  // k_front (front.cuh) takes the big frames; ATSC_FRONT=0 keeps the separate passes
+    // ATSC_FRONT=1: k_front (front.cuh) takes the big frames in one read.  Off by default: on B200 the fused
+    // kernel is issue bound (profiles/r2_front_*.md) and, holding an SM's whole shared memory, cannot overlap the
+    // other engines' waves, so the separate passes are still the faster pipeline (1.85 vs 2.15 ms per bench step)
+    bool front = false;
+    bool front_fold = true;  // ... including the FFT probe (ATSC_FRONT_FOLD=0: k_fft_fwd's own probe reads the samples again)
     Engine eng[MAX_ENGINES];
     uint64_t wave_samples = 0;
     double *inv_d2 = nullptr;
@@ -392,7 +394,8 @@ int device_init(Device &D) {
     // waves in flight per device and samples per wave (tunable for experiments)
     D.n_engines = env_int("ATSC_ENGINES", 4, 1, MAX_ENGINES);
     D.wave_samples = (uint64_t)env_int("ATSC_WAVE_MI", 72, 1, 512) << 20;
-    D.front = env_int("ATSC_FRONT", 1, 0, 1) != 0;
+    D.front = env_int("ATSC_FRONT", 0, 0, 1) != 0;
+    D.front_fold = env_int("ATSC_FRONT_FOLD", 1, 0, 1) != 0;
     D.sms = sms;
     if ((rc = engine_init(D, D.eng[0], sms))) return rc;  // the others are set up when a call first needs them
     CK(cudaEventCreate(&D.ev_begin));
@@ -415,7 +418,7 @@ void device_free(Device &D) {
                         P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.poly_slope, P.dec_pts,
                         P.dec_mark, P.dec_idx, E.queues, E.d_ctl, E.d_frames, E.d_samples, E.d_arena, E.d_payload,
                         E.d_dec, E.d_pay_in, E.d_out, E.d_status, E.d_spec_xd, E.d_spec_keys, E.d_chunks, E.d_parts,
-                        E.d_items, E.d_fold};
+                        E.d_items};
         for (void *p : ptrs)
             if (p) cudaFree(p);
         void *hp[] = {E.h_ctl, E.h_frames, E.h_dec, E.h_status, E.h_chunks, E.h_items};
@@ -507,7 +510,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     hcap = E.items_cap;
     if ((rc = grow(D, E.st, E.d_items, E.items_cap, n_items))) return rc;
     if ((rc = grow(D, E.st, E.h_items, hcap, E.items_cap, true))) return rc;
-    uint32_t nc = 0, ni = 0, nfold = 0;
+    uint32_t nc = 0, ni = 0;
     for (uint32_t i = 0; i < n; i++) {
         FrameWork &f = E.h_frames[i];
         memset(&f, 0, sizeof f);
@@ -551,11 +554,10 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
                 if (G.T4) {
                     f.spec_off = spec;
                     spec += G.M + 8;
-                    // Auto frames that k_front streams also get the probe's stage-1 fold there
-                    if ((f.front_mode & FM_ON) && r.bounded && r.comp == C_AUTO && r.forced == 0xFF && !r.select_only &&
+                    // Auto frames that k_front streams also get the FFT probe there
+                    if (D.front_fold && (f.front_mode & FM_ON) && r.bounded && r.comp == C_AUTO && r.forced == 0xFF && !r.select_only &&
                         f2_fold_ra(G.M1) && ((L - r.len) / 2) % 2 == 0) {
                         f.front_mode |= FM_FOLD;
-                        f.fold_idx = nfold++;
                     }
                 }
             }
@@ -567,7 +569,6 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
             arena += cap;
         }
     }
-    if ((rc = grow(D, E.st, E.d_fold, E.fold_cap, (size_t)nfold * FRONT_FOLD_SLOTS + 1))) return rc;
     if ((rc = sync_geoms(D))) return rc;
     if ((rc = grow(D, E.st, E.d_arena, E.arena_cap, (size_t)arena + 1))) return rc;
     if ((rc = grow(D, E.st, E.d_spec_xd, E.spec_xd_cap, (size_t)spec + 1))) return rc;
@@ -583,7 +584,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     CK(cudaMemsetAsync(E.d_ctl, 0, sizeof(WaveCtl), st));
     CK(cudaEventRecord(E.ev[12], st));
     if (n_items) {
-        launch_front(E.d_frames, E.d_items, (uint32_t)n_items, d_samples, max_err, D.geoms_dev, E.d_fold, E.queues + 9, st);
+        launch_front(E.d_frames, E.d_items, (uint32_t)n_items, d_samples, max_err, D.geoms_dev, E.pool, E.queues + 9, st);
         D.launches++;
     }
     CK(cudaEventRecord(E.ev[13], st));
@@ -602,8 +603,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     }
     CK(cudaEventRecord(E.ev[10], st));
     if (spec) {
-        launch_fft_fwd(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_spec_xd, E.d_spec_keys, E.d_fold,
-                       E.queues + 7, st);
+        launch_fft_fwd(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_spec_xd, E.d_spec_keys, E.queues + 7, st);
         D.launches++;
     }
     CK(cudaEventRecord(E.ev[11], st));

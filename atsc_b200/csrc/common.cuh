@@ -62,7 +62,7 @@ struct FrameWork {
     uint32_t aux_size;   // Noop / Constant payload size
     uint32_t fwd_done;   // k_fft_fwd left the half spectrum + keys at spec_off
     uint32_t chunk0;     // first entry of this frame in the wave's stats chunk table
-    uint32_t fold_idx;   // FM_FOLD frames: slot in the wave's fold arena
+    uint32_t pad3;
     uint64_t spec_off;   // entry offset into the wave's spectrum arena (~0 = frame not eligible for fft2.cuh)
     // ---- result
     uint8_t winner, near_tie;

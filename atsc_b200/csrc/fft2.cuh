@@ -620,8 +620,9 @@ __device__ inline uint32_t f2_probe(const double *__restrict__ d, int N, int pre
 }
 
 // ---------------------------------------------------------------------------------------
-// PROBE from a stored fold: k_front (front.cuh) leaves the two folds (A, B) of every slot
-// m = p*243 + c < RB*243 as one float4  fold[m] = (A.x, A.y, B.x, B.y).  What remains is fold_out,
+// PROBE from a fold: k_front (front.cuh) accumulates the two folds (A, B) of every slot
+// m = p*243 + c < RB*243 as one float4  fold[m] = (A.x, A.y, B.x, B.y) in shared memory and runs
+// the rest of the probe at the end of the frame.  What remains is fold_out,
 // the Stockham twiddle, pass-1 stage 2 for the two families and pass 2 for the 2*RB probed rows.
 // ---------------------------------------------------------------------------------------
 template <int RA, int RB>
@@ -636,7 +637,7 @@ __device__ inline void f2_fold_stage2(const float4 *__restrict__ fold, const flo
 #pragma unroll
         for (int t = 0; t < RB; t++) {
             float2 s1, sR;
-            fold_out(__ldcg(fold + t * F2_M2 + c), s1, sR);
+            fold_out(fold[t * F2_M2 + c], s1, sR);  // shared memory (k_front) or global
             b[t] = cmul(fam ? sR : s1, __ldg(tw1 + t * q));
         }
         DftS<RB, 1, false>::run(b);

@@ -8,9 +8,9 @@
 //   * the MAPE of the FIRST Polynomial candidate step, which is known before the stats are
 //     (step = N / max(3, N/100) = 100 for every frame this kernel takes; polynomial.rs:209-277,
 //     utils/error.rs:104-116),
-//   * stage 1 of the FFT probe: the folds over the RA contiguous chunks of the padded frame
-//     (fft2.cuh: fold_acc) from which "at least c nonzero bins" is later proven without touching
-//     the samples again (fft.rs:249-252; pruning rule of frame/mod.rs:94-147).
+//   * the FFT probe: stage 1 (the folds over the RA contiguous chunks of the padded frame, fft2.cuh:
+//     fold_acc) while streaming, the rest at the end of the frame, which proves "at least c nonzero
+//     bins" without touching the samples again (fft.rs:249-252; pruning rule of frame/mod.rs:94-147).
 // A frame whose Polynomial candidate passes at its first step and whose FFT candidate is pruned --
 // every big frame of a monitoring fleet -- never sees k_poly / the sample-reading probe.
 //
@@ -30,6 +30,7 @@
 #include "common.cuh"
 #include "fft2.cuh"
 #include "poly.cuh"
+#include "rle.cuh"
 #include "stats.cuh"
 
 namespace atsc {
@@ -76,7 +77,7 @@ struct FrontSmem {
     StatsPart part;
     double s249, s250, lastv;      // samples captured while streaming
     double fin_vmin, fin_vmax;     // the frame's final range, for the whole CTA
-    uint32_t fin_flags;            // bit0 need_poly (Catmull-Rom), bit1 need_fft, bits 8.. bitdepth
+    uint32_t fin_flags;            // bit0 need_poly (Catmull-Rom), bit1 need_fft, bit2 work was skipped, bit3 ... and missed, bits 8.. bitdepth
     uint32_t list_n;
     uint32_t varied[2];
 };
@@ -338,8 +339,8 @@ __device__ inline void front_claim(FrontDesc *D, const FrameWork *fr, const uint
 // never drains between frames.
 __device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ items, uint32_t n_items, uint32_t fc,
                                    const double *__restrict__ samples, double max_err, const FftGeom *__restrict__ geoms,
-                                   float4 *fold_arena, unsigned *q, FrontSmem *sm, uint32_t &fill, uint32_t &use,
-                                   uint32_t &issued, uint32_t nap) {
+                                   float2 *W, unsigned *q, FrontSmem *sm, uint32_t &fill, uint32_t &use, uint32_t &issued,
+                                   uint32_t nap) {
     const uint32_t t = threadIdx.x, lane = t & 31u;
     constexpr uint32_t T = FR_THREADS;
     const bool compute = t < T;
@@ -617,7 +618,9 @@ __device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ i
             if (skipped && seen_var) fw->front_mode = mode & ~FM_FOLD;  // the fold misses tiles: old probe
             sm->fin_vmin = fw->vmin;
             sm->fin_vmax = fw->vmax;
-            sm->fin_flags = ((fw->need_poly && fw->poly_type == 0) ? 1u : 0u) | (fw->need_fft ? 2u : 0u) | ((uint32_t)fw->bitdepth << 8);
+            // decisions for the whole CTA (the producer warp did not stream: its `skipped` / `seen_var` say nothing)
+            sm->fin_flags = ((fw->need_poly && fw->poly_type == 0) ? 1u : 0u) | (fw->need_fft ? 2u : 0u) | (skipped ? 4u : 0u) |
+                            ((skipped && seen_var) ? 8u : 0u) | ((uint32_t)fw->bitdepth << 8);
         }
         __syncthreads();
     }
@@ -637,7 +640,7 @@ __device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ i
                 fw->poly_err = 0.0;
                 fw->poly_valid = 1;
             }
-        } else if (!skipped && poly_tame(vmin, vmax) && sm->list_n <= FR_LIST && f.K >= 4u) {
+        } else if (!(fin & 4u) && poly_tame(vmin, vmax) && sm->list_n <= FR_LIST && f.K >= 4u) {
             // parked samples: the generic arithmetic with the frame's final clamp
             auto pts = [&](uint32_t qk) { return d[poly_pos(k, qk)]; };
             const uint32_t nl = sm->list_n;
@@ -650,7 +653,7 @@ __device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ i
             const double target = round_f64_dec(max_err, 3);
             const bool pass = !(target < round_f64_dec(cur, 4));  // polynomial.rs:231: the loop ends here
             uint32_t size = 0;
-            if (pass) size = poly_payload_size(d, k, (int)(fin >> 8), false, reinterpret_cast<uint32_t *>(sm->red));
+            if (pass) size = poly_payload_size(d, k, (int)((fin >> 8) & 0xFFu), false, reinterpret_cast<uint32_t *>(sm->red));
             if (t == 0) {
                 fw->poly_step = FR_STEP;
                 fw->poly_err = cur;
@@ -666,17 +669,43 @@ __device__ inline void front_frame(FrameWork *fr, const uint32_t *__restrict__ i
             }
         }
     }
-    // ======================= fold -> arena =======================
-    if (do_fold && !(skipped && seen_var) && (fin & 2u)) {
+    // ======================= FFT probe from the fold =======================
+    // (the rule of k_fft_fwd: the first schedule point keeps c1 = min(max_freq, #nonzero bins) entries,
+    // fft.rs:249-252, and the payload only grows from there; FFT wins only with size <= the passing
+    // candidates after it, frame/mod.rs:94-147)
+    if (do_fold && !(fin & 8u) && (fin & 2u)) {
         // the gibbs suffix replicates the last sample: the last chunk of the slots from (prefix + N) / 2 on
         const float lastf = (float)sm->lastv;
         const float2 w = sm->root[RA - 1u];
         const uint32_t m0 = ((f.prefix + f.N) >> 1) - (RA - 1u) * f.Cc;
-        float4 *dst = fold_arena + (size_t)fw->fold_idx * FR_FOLD_SLOTS;
-        for (uint32_t m = t; m < f.Cc; m += FR_CTA) {
+        for (uint32_t m = m0 + t; m < f.Cc; m += FR_CTA) {
             float4 ab = sm->fold[m];
-            if (m >= m0) fold_acc(ab, lastf, lastf, w);
-            __stcg(dst + m, ab);
+            fold_acc(ab, lastf, lastf, w);
+            sm->fold[m] = ab;
+        }
+        __syncthreads();
+        const FftGeom &G = geoms[fw->geom];
+        // stage 2 reads the fold and writes the probe intermediate to W (L2); pass 2 then reuses the fold's memory
+        const uint32_t nzl = f2_probe_from_fold(sm->fold, G, W, reinterpret_cast<float2 *>(sm->fold));
+        const uint32_t nz = block_sum_u32(nzl, reinterpret_cast<uint32_t *>(sm->red));
+        if (t == 0) {
+            uint32_t bound = 0xFFFFFFFFu;
+            if (fw->poly_valid == 1 && fw->poly_err <= max_err) bound = min(bound, fw->poly_size);
+            if (fw->need_rle) bound = min(bound, rle_upper_bound(fw));  // RLE's error is 0: it always passes
+            const uint32_t mf = (3u >= f.N / 100u) ? 3u : f.N / 100u;
+            const uint32_t cap = min(fw->fft_list_cap, (uint32_t)FFT_KCAP);
+            const uint32_t smax = G.Bn > 65536u ? 502u : 251u;
+            const uint32_t c1 = min(min(mf, nz), cap);
+            if (bound != 0xFFFFFFFFu && fft_payload_size(c1, min(c1, smax)) > bound) {
+                fw->fft_count = c1;
+                fw->fft_err = max_err + 1.0;
+                fw->fft_size = 0;
+                fw->fft_iters = 1;
+                fw->fft_tie = 0;
+                fw->fft_valid = 2;  // proven unable to win
+            } else {
+                fw->front_mode = mode & ~FM_FOLD;  // sparse spectrum: k_fft_fwd counts every bin
+            }
         }
     }
     __syncthreads();

@@ -73,7 +73,7 @@ __global__ void k_plan(FrameWork *fr, uint32_t n, const double *__restrict__ sam
 // ONE pass over the samples, staged through shared memory by bulk asynchronous copies.
 __global__ void __launch_bounds__(FR_CTA, 1) k_front(FrameWork *fr, const uint32_t *__restrict__ items, uint32_t n_items,
                                                      const double *__restrict__ samples, double max_err,
-                                                     const FftGeom *__restrict__ geoms, float4 *fold_arena, unsigned *q,
+                                                     const FftGeom *__restrict__ geoms, SlotPool pool, unsigned *q,
                                                      uint32_t nap) {
     extern __shared__ __align__(128) unsigned char dyn_front[];
     FrontSmem *sm = reinterpret_cast<FrontSmem *>(dyn_front);
@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(FR_CTA, 1) k_front(FrameWork *fr, const uint32
     __syncthreads();
     for (uint32_t fc = 0;; fc++) {
         if (sm->desc[fc & 1u].idx >= n_items) break;  // the producer claims the next item while a frame streams
-        front_frame(fr, items, n_items, fc, samples, max_err, geoms, fold_arena, q, sm, fill, use, issued, nap);
+        front_frame(fr, items, n_items, fc, samples, max_err, geoms, pool.fft_W + (size_t)blockIdx.x * MAX_FFT_LEN, q, sm, fill,
+                    use, issued, nap);
     }
 }
 
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fft_small(FrameWork *fr, uint32_
 __global__ void __launch_bounds__(F2_THREADS, 2) k_fft_fwd(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
                                                            double max_err, const FftGeom *__restrict__ geoms,
                                                            SlotPool pool, float2 *spec_xd, uint32_t *spec_keys,
-                                                           const float4 *__restrict__ fold_arena, unsigned *q) {
+                                                           unsigned *q) {
     extern __shared__ float2 dyn_f2[];
     __shared__ uint32_t sh[40];
     __shared__ FftGeom sg;
@@ -424,6 +425,7 @@ __global__ void __launch_bounds__(F2_THREADS, 2) k_fft_fwd(FrameWork *fr, uint32
         if (i >= (int)n) break;
         FrameWork *fw = &fr[i];
         if (!fw->need_fft || fw->f32_const || fw->geom < 0 || fw->spec_off == ~0ull) continue;
+        if (fw->fft_valid == 2) continue;  // k_front's probe already proved that the candidate cannot win
         if (t == 0) sg = geoms[fw->geom];
         __syncthreads();
         const uint32_t N = fw->len;
@@ -445,10 +447,7 @@ __global__ void __launch_bounds__(F2_THREADS, 2) k_fft_fwd(FrameWork *fr, uint32
             const uint32_t mf = (3 >= N / 100) ? 3 : N / 100;
             const uint32_t cap = min(fw->fft_list_cap, (uint32_t)FFT_KCAP);
             const uint32_t smax = sg.Bn > 65536u ? 502u : 251u;
-            // frames that went through k_front bring the probe's stage-1 fold with them: no sample is read
-            uint32_t nz = (fw->front_mode & FM_FOLD)
-                              ? block_sum_u32(f2_probe_from_fold(fold_arena + (size_t)fw->fold_idx * FR_FOLD_SLOTS, sg, W, dyn_f2), sh)
-                              : block_sum_u32(f2_probe(samples + fw->off, (int)N, (int)prefix, sg, W, dyn_f2), sh);
+            uint32_t nz = block_sum_u32(f2_probe(samples + fw->off, (int)N, (int)prefix, sg, W, dyn_f2), sh);
             uint32_t c1 = min(min(mf, nz), cap);
             bool pruned = fft_payload_size(c1, min(c1, smax)) > bound;
             if (!pruned) {
@@ -1152,17 +1151,16 @@ void launch_fft_small(FrameWork *fr, uint32_t n, const double *samples, double m
     k_fft_small<<<grid_for(n, 8 * sms()), FS_THREADS, fs_smem_bytes(lmax), st>>>(fr, n, samples, max_err, geoms, arena, lmax, q);
 }
 void launch_fft_fwd(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
-                    SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, const float4 *fold_arena, unsigned *q,
-                    cudaStream_t st) {
+                    SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st) {
     k_fft_fwd<<<grid_for(n, pool.fwd_slots), F2_THREADS, F2_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool,
-                                                                             spec_xd, spec_keys, fold_arena, q);
+                                                                             spec_xd, spec_keys, q);
 }
 void launch_front(FrameWork *fr, const uint32_t *items, uint32_t n_items, const double *samples, double max_err,
-                  const FftGeom *geoms, float4 *fold_arena, unsigned *q, cudaStream_t st) {
+                  const FftGeom *geoms, SlotPool pool, unsigned *q, cudaStream_t st) {
     // back-off (ns) of the producer lane's wait for a free ring slot (tunable for experiments)
     static const uint32_t nap = getenv("ATSC_FRONT_NAP") ? (uint32_t)atoi(getenv("ATSC_FRONT_NAP")) : 64u;
-    k_front<<<grid_for(n_items, sms()), FR_CTA, FRONT_SMEM_BYTES, st>>>(fr, items, n_items, samples, max_err, geoms,
-                                                                        fold_arena, q, nap);
+    k_front<<<grid_for(n_items, sms()), FR_CTA, FRONT_SMEM_BYTES, st>>>(fr, items, n_items, samples, max_err, geoms, pool, q,
+                                                                        nap);
 }
 void launch_noop_size(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st) {
     k_noop_size<<<grid_for(n, 2 * sms()), BLOCK, 0, st>>>(fr, n, samples, q);

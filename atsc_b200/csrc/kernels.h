@@ -55,13 +55,11 @@ void launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err
 void launch_fft_small(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
                       FftEntry *arena, uint32_t lmax, unsigned *q, cudaStream_t st);
 void launch_fft_fwd(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
-                    SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, const float4 *fold_arena, unsigned *q,
-                    cudaStream_t st);
+                    SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st);
 // fused front end (front.cuh) of the frames items[0 .. n_items): frames with FM_ON set by the host
 void launch_front(FrameWork *fr, const uint32_t *items, uint32_t n_items, const double *samples, double max_err,
-                  const FftGeom *geoms, float4 *fold_arena, unsigned *q, cudaStream_t st);
+                  const FftGeom *geoms, SlotPool pool, unsigned *q, cudaStream_t st);
 constexpr uint32_t FRONT_MIN_SAMPLES = 16384;  // == FRONT_MIN_LEN (front.cuh)
-constexpr uint32_t FRONT_FOLD_SLOTS = 18 * 243;  // == FR_FOLD_SLOTS: float4 (A, B) per frame in the fold arena
 void launch_noop_size(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st);
 void launch_select(FrameWork *fr, uint32_t n, double max_err, cudaStream_t st);
 void launch_scan(FrameWork *fr, uint32_t n, unsigned long long *total, cudaStream_t st);

@@ -19,7 +19,11 @@ def ctxs():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import atsc_b200
-    on = atsc_b200.Context()
+    os.environ["ATSC_FRONT"] = "1"  # the fused front end is opt-in
+    try:
+        on = atsc_b200.Context()
+    finally:
+        os.environ.pop("ATSC_FRONT")
     os.environ["ATSC_FRONT"] = "0"
     try:
         off = atsc_b200.Context()
