@@ -58,6 +58,7 @@ struct WaveJob {
 
 struct Engine {
     cudaStream_t st = nullptr;
+    bool ready = false;  // every workspace allocated (a partly set-up engine is torn down, never used)
     SlotPool pool{};
     unsigned *queues = nullptr;
     WaveCtl *d_ctl = nullptr, *h_ctl = nullptr;
@@ -113,6 +114,9 @@ struct Device {
     FftGeom *geoms_dev = nullptr;  // GEOM_CAP entries, appended to (never reallocated: waves in flight read it)
     size_t geoms_uploaded = 0;
     uint64_t launches = 0;
+    // multi-device calls: page-locked staging of this device's share of the payload bytes
+    uint8_t *h_stage = nullptr;
+    size_t h_stage_cap = 0;
     // device span of the last compress / decompress call: first operation issued -> last one done
     cudaEvent_t ev_begin = nullptr, ev_end[MAX_ENGINES] = {};
     double last_call_ms = 0.0;
@@ -143,6 +147,20 @@ namespace {
             return ATSC_ERR_CUDA;                                                                  \
         }                                                                                          \
     } while (0)
+
+// inside the wave loops: record the error and leave the loop, so that the common tail still drains every
+// engine (async copies into the caller's buffers must not outlive the call)
+#define CKB(call)                                                                                  \
+    {                                                                                              \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char b__[512];                                                                         \
+            snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            D.err = b__;                                                                           \
+            rc = ATSC_ERR_CUDA;                                                                    \
+            break;                                                                                 \
+        }                                                                                          \
+    }
 
 // grows a buffer that only the engine's own stream touches: the stream is drained first so no
 // kernel of an earlier wave still uses the old allocation
@@ -336,8 +354,25 @@ int sync_geoms(Device &D) {
 }
 
 // ---------------------------------------------------------------- device setup
-int engine_init(Device &D, Engine &E, int sms) {
-    if (E.st) return ATSC_OK;  // already set up
+void engine_free(Engine &E) {
+    SlotPool &P = E.pool;
+    void *ptrs[] = {P.rle_k0, P.rle_k1, P.rle_i0, P.rle_i1, P.rle_bnd, P.fft_W, P.fft_Xd, P.fft_keys, P.fft_rank,
+                    P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.poly_slope, P.dec_pts,
+                    P.dec_mark, P.dec_idx, E.queues, E.d_ctl, E.d_frames, E.d_samples, E.d_arena, E.d_payload,
+                    E.d_dec, E.d_pay_in, E.d_out, E.d_status, E.d_spec_xd, E.d_spec_keys, E.d_chunks, E.d_parts,
+                    E.d_items};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    void *hp[] = {E.h_ctl, E.h_frames, E.h_dec, E.h_status, E.h_chunks, E.h_items};
+    for (void *p : hp)
+        if (p) cudaFreeHost(p);
+    for (auto &ev : E.ev)
+        if (ev) cudaEventDestroy(ev);
+    if (E.st) cudaStreamDestroy(E.st);
+    E = Engine{};
+}
+
+int engine_alloc(Device &D, Engine &E, int sms) {
     CK(cudaStreamCreateWithFlags(&E.st, cudaStreamNonBlocking));
     SlotPool &P = E.pool;
     P.rle_slots = 2 * sms;
@@ -371,6 +406,21 @@ int engine_init(Device &D, Engine &E, int sms) {
     CK(cudaMalloc((void **)&E.queues, 64 * sizeof(unsigned)));
     CK(cudaMalloc((void **)&E.d_ctl, sizeof(WaveCtl)));
     CK(cudaMallocHost((void **)&E.h_ctl, sizeof(WaveCtl)));
+    return ATSC_OK;
+}
+
+// ~3.4 GB of workspaces per engine.  An allocation can fail in the middle of a call (engines are set up when
+// a call first reaches them, and cudaErrorMemoryAllocation is not sticky): the engine is then torn down
+// completely, so a later call neither launches on null workspaces nor leaks the part that was allocated.
+int engine_init(Device &D, Engine &E, int sms) {
+    if (E.ready) return ATSC_OK;
+    int rc = engine_alloc(D, E, sms);
+    if (rc) {
+        cudaGetLastError();
+        engine_free(E);
+        return rc;
+    }
+    E.ready = true;
     return ATSC_OK;
 }
 
@@ -411,40 +461,29 @@ int device_init(Device &D) {
 void device_free(Device &D) {
     cudaSetDevice(D.id);
     cudaDeviceSynchronize();
-    for (int e = 0; e < D.n_engines; e++) {
-        Engine &E = D.eng[e];
-        SlotPool &P = E.pool;
-        void *ptrs[] = {P.rle_k0, P.rle_k1, P.rle_i0, P.rle_i1, P.rle_bnd, P.fft_W, P.fft_Xd, P.fft_keys, P.fft_rank,
-                        P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.poly_slope, P.dec_pts,
-                        P.dec_mark, P.dec_idx, E.queues, E.d_ctl, E.d_frames, E.d_samples, E.d_arena, E.d_payload,
-                        E.d_dec, E.d_pay_in, E.d_out, E.d_status, E.d_spec_xd, E.d_spec_keys, E.d_chunks, E.d_parts,
-                        E.d_items};
-        for (void *p : ptrs)
-            if (p) cudaFree(p);
-        void *hp[] = {E.h_ctl, E.h_frames, E.h_dec, E.h_status, E.h_chunks, E.h_items};
-        for (void *p : hp)
-            if (p) cudaFreeHost(p);
-        for (auto &ev : E.ev)
-            if (ev) cudaEventDestroy(ev);
-        if (E.st) cudaStreamDestroy(E.st);
-    }
+    for (int e = 0; e < D.n_engines; e++) engine_free(D.eng[e]);
     if (D.ev_begin) cudaEventDestroy(D.ev_begin);
     for (auto &ev : D.ev_end)
         if (ev) cudaEventDestroy(ev);
+    if (D.h_stage) cudaFreeHost(D.h_stage);
     if (D.inv_d2) cudaFree(D.inv_d2);
     if (D.geoms_dev) cudaFree(D.geoms_dev);
     for (void *p : D.geom_allocs) cudaFree(p);
     if (D.st) cudaStreamDestroy(D.st);
 }
 
-bool is_device_ptr(const void *p) {
+// device memory (or managed): *device = the GPU that owns it
+bool is_device_ptr(const void *p, int *device = nullptr) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
+    if (device) *device = a.device;
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
+// the context's Device that owns a device-resident buffer; nullptr when that GPU is not part of the context
+Device *owner_of(atsc_ctx *ctx, int device);
 
 // device span of a call: begin is recorded on the first engine's stream before anything is issued,
 // an end event on every engine's stream after its last operation
@@ -764,15 +803,20 @@ int compress_on_device(Device &D, const double *samples, bool dev_ptr, const uin
             packed = span > 2 * tot + 4096;
             if ((rc = grow(D, E.st, E.d_samples, E.samples_cap, (size_t)(packed ? tot : span) + 8))) break;
             if (!packed) {
-                CK(cudaMemcpyAsync(E.d_samples, samples + lo, span * 8, cudaMemcpyHostToDevice, E.st));
+                CKB(cudaMemcpyAsync(E.d_samples, samples + lo, span * 8, cudaMemcpyHostToDevice, E.st));
             } else {
                 uint64_t o = 0;
-                for (uint32_t k = pos; k < end; k++) {
+                for (uint32_t k = pos; k < end && !rc; k++) {
                     uint32_t fi = idx[k];
-                    CK(cudaMemcpyAsync(E.d_samples + o, samples + frame_off[fi], (size_t)frame_len[fi] * 8,
-                                       cudaMemcpyHostToDevice, E.st));
+                    cudaError_t ce = cudaMemcpyAsync(E.d_samples + o, samples + frame_off[fi], (size_t)frame_len[fi] * 8,
+                                                     cudaMemcpyHostToDevice, E.st);
+                    if (ce != cudaSuccess) {
+                        D.err = std::string("cudaMemcpyAsync (packed samples): ") + cudaGetErrorString(ce);
+                        rc = ATSC_ERR_CUDA;
+                    }
                     o += frame_len[fi];
                 }
+                if (rc) break;
             }
             d_samples = E.d_samples;
         }
@@ -836,8 +880,11 @@ int compress_on_device(Device &D, const double *samples, bool dev_ptr, const uin
         if (rc2) rc = rc2;
         E.job.active = false;
     }
-    int rc3 = span_end(D);
+    int rc3 = span_end(D);  // synchronises every engine's stream, also on the error path
     if (!rc) rc = rc3;
+    if (rc)
+        for (int k = 0; k < D.n_engines; k++)
+            if (D.eng[k].st) cudaStreamSynchronize(D.eng[k].st);
     if (!rc) CK(cudaGetLastError());
     return rc;
 }
@@ -920,15 +967,15 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
             }
         }
         if (rc || (rc = sync_geoms(D))) break;
-        CK(cudaMemcpyAsync(E.d_dec, E.h_dec, (size_t)n * sizeof(DecFrame), cudaMemcpyHostToDevice, E.st));
-        CK(cudaMemcpyAsync(E.d_pay_in, payloads + plo, (size_t)(phi - plo), cudaMemcpyHostToDevice, E.st));
-        CK(cudaMemsetAsync(E.queues, 0, 64 * sizeof(unsigned), E.st));
+        CKB(cudaMemcpyAsync(E.d_dec, E.h_dec, (size_t)n * sizeof(DecFrame), cudaMemcpyHostToDevice, E.st));
+        CKB(cudaMemcpyAsync(E.d_pay_in, payloads + plo, (size_t)(phi - plo), cudaMemcpyHostToDevice, E.st));
+        CKB(cudaMemsetAsync(E.queues, 0, 64 * sizeof(unsigned), E.st));
         double *d_out = out_dev ? out : E.d_out;
-        CK(cudaEventRecord(E.ev[8], E.st));
+        CKB(cudaEventRecord(E.ev[8], E.st));
         launch_decode(E.d_dec, n, E.d_pay_in, d_out, D.geoms_dev, E.pool, D.inv_d2, E.d_status, E.queues + 6, E.st);
-        CK(cudaEventRecord(E.ev[9], E.st));
+        CKB(cudaEventRecord(E.ev[9], E.st));
         D.launches++;
-        CK(cudaMemcpyAsync(E.h_status, E.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, E.st));
+        CKB(cudaMemcpyAsync(E.h_status, E.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, E.st));
         if (!out_dev) {
             // coalesce frames that are adjacent in the caller's output
             uint32_t k = 0;
@@ -941,10 +988,16 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
                     len += frames[idx[pos + j]].sample_count;
                     j++;
                 }
-                CK(cudaMemcpyAsync(out + dst, E.d_out + src, len * 8, cudaMemcpyDeviceToHost, E.st));
+                cudaError_t ce = cudaMemcpyAsync(out + dst, E.d_out + src, len * 8, cudaMemcpyDeviceToHost, E.st);
+                if (ce != cudaSuccess) {
+                    D.err = std::string("cudaMemcpyAsync (decoded samples): ") + cudaGetErrorString(ce);
+                    rc = ATSC_ERR_CUDA;
+                    break;
+                }
                 src += len;
                 k = j;
             }
+            if (rc) break;
         }
         E.dec_active = true;
         E.dec_pos = pos;
@@ -957,8 +1010,11 @@ int decompress_on_device(Device &D, const atsc_frame_in *frames, const uint32_t 
         if (rc2) rc = rc2;
         E.dec_active = false;
     }
-    int rc3 = span_end(D);
+    int rc3 = span_end(D);  // synchronises every engine's stream, also on the error path
     if (!rc) rc = rc3;
+    if (rc)
+        for (int k = 0; k < D.n_engines; k++)
+            if (D.eng[k].st) cudaStreamSynchronize(D.eng[k].st);
     return rc;
 }
 
@@ -970,6 +1026,12 @@ std::vector<std::vector<uint32_t>> shard(const uint32_t *lens, uint32_t n, size_
     for (size_t d = 0; d < ndev; d++)
         for (uint32_t i = first[d]; i < first[d + 1]; i++) parts[d].push_back(i);
     return parts;
+}
+
+Device *owner_of(atsc_ctx *ctx, int device) {
+    for (Device *D : ctx->devs)
+        if (D->id == device) return D;
+    return nullptr;
 }
 
 }  // namespace
@@ -1078,13 +1140,20 @@ int atsc_gpu_compress_frames(atsc_ctx *ctx, const double *samples, const uint64_
             ctx->err = "frame_len must be 1..131072 (optimizer/mod.rs:27)";
             return ATSC_ERR_ARG;
         }
-    const bool dev_ptr = is_device_ptr(samples);
+    int owner = -1;
+    const bool dev_ptr = is_device_ptr(samples, &owner);
     const size_t nd = dev_ptr ? 1 : ctx->devs.size();
     if (nd == 1) {
+        // device-resident samples are compressed by the GPU that owns them
+        Device *Dp = dev_ptr ? owner_of(ctx, owner) : ctx->devs[0];
+        if (!Dp) {
+            ctx->err = "samples live on a GPU that is not part of this context";
+            return ATSC_ERR_ARG;
+        }
         std::vector<uint32_t> idx(n_frames);
         for (uint32_t i = 0; i < n_frames; i++) idx[i] = i;
         PayloadSink sink{payload_buf, payload_cap, 0, false};
-        Device &D = *ctx->devs[0];
+        Device &D = *Dp;
         int rc = compress_on_device(D, samples, dev_ptr, frame_off, frame_len, idx.data(), n_frames, compressor,
                                     max_error, speed, bounded, out, sink);
         if (rc) {
@@ -1098,21 +1167,41 @@ int atsc_gpu_compress_frames(atsc_ctx *ctx, const double *samples, const uint64_
         }
         return ATSC_OK;
     }
-    // several devices: contiguous frame ranges, one host thread per device, no collective
+    // Several devices: contiguous frame ranges, one host thread per device, no collective (frames never
+    // communicate; the reference stitches sequentially, data.rs:73-75).  Each device's payload lands in its
+    // own page-locked staging buffer (~2 B per sample, grown and the share redone if a fleet needs more),
+    // then the shares are laid end to end in the caller's buffer.
     auto parts = shard(frame_len, n_frames, nd);
-    std::vector<std::vector<uint8_t>> bufs(nd);
     std::vector<PayloadSink> sinks(nd);
     std::vector<int> rcs(nd, 0);
     std::vector<std::thread> th;
     for (size_t d = 0; d < nd; d++) {
-        uint64_t cap = 0;
-        for (uint32_t i : parts[d]) cap += (uint64_t)frame_len[i] * 16 + 64;  // worst case: RLE of all-distinct f64
-        bufs[d].resize(cap);
-        sinks[d] = PayloadSink{bufs[d].data(), cap, 0, false};
         th.emplace_back([&, d]() {
             if (parts[d].empty()) return;
-            rcs[d] = compress_on_device(*ctx->devs[d], samples, false, frame_off, frame_len, parts[d].data(),
-                                        (uint32_t)parts[d].size(), compressor, max_error, speed, bounded, out, sinks[d]);
+            Device &D = *ctx->devs[d];
+            uint64_t ns = 0;
+            for (uint32_t i : parts[d]) ns += frame_len[i];
+            uint64_t cap = ns * 2 + 64 * (uint64_t)parts[d].size() + (1u << 20);
+            for (int attempt = 0; attempt < 2; attempt++) {
+                if (cap > D.h_stage_cap) {
+                    cudaSetDevice(D.id);
+                    if (D.h_stage) cudaFreeHost(D.h_stage);
+                    D.h_stage = nullptr;
+                    D.h_stage_cap = 0;
+                    if (cudaMallocHost((void **)&D.h_stage, cap) != cudaSuccess) {
+                        cudaGetLastError();
+                        D.err = "cannot allocate page-locked payload staging";
+                        rcs[d] = ATSC_ERR_CUDA;
+                        return;
+                    }
+                    D.h_stage_cap = cap;
+                }
+                sinks[d] = PayloadSink{D.h_stage, D.h_stage_cap, 0, false};
+                rcs[d] = compress_on_device(D, samples, false, frame_off, frame_len, parts[d].data(), (uint32_t)parts[d].size(),
+                                            compressor, max_error, speed, bounded, out, sinks[d]);
+                if (rcs[d] || !sinks[d].overflow) return;
+                cap = sinks[d].used + 64;  // the share needs this much: once more
+            }
         });
     }
     for (auto &t : th) t.join();
@@ -1127,7 +1216,7 @@ int atsc_gpu_compress_frames(atsc_ctx *ctx, const double *samples, const uint64_
         if (used + sinks[d].used > payload_cap)
             overflow = true;
         else if (sinks[d].used)
-            memcpy(payload_buf + used, bufs[d].data(), sinks[d].used);
+            memcpy(payload_buf + used, sinks[d].buf, sinks[d].used);
         used += sinks[d].used;
     }
     if (payload_used) *payload_used = used;
@@ -1151,15 +1240,25 @@ int atsc_gpu_decompress_frames(atsc_ctx *ctx, const atsc_frame_in *frames, uint3
             ctx->err = "frame compressor must be a concrete compressor (reference: todo!())";
             return ATSC_ERR_UNSUPPORTED;
         }
-    const bool out_dev = is_device_ptr(out_samples);
+    int owner = -1;
+    const bool out_dev = is_device_ptr(out_samples, &owner);
     const size_t nd = out_dev ? 1 : ctx->devs.size();
+    Device *D0 = out_dev ? owner_of(ctx, owner) : ctx->devs[0];
+    if (!D0) {
+        ctx->err = "out_samples lives on a GPU that is not part of this context";
+        return ATSC_ERR_ARG;
+    }
     std::vector<uint32_t> lens(n_frames);
     for (uint32_t i = 0; i < n_frames; i++) lens[i] = frames[i].sample_count;
     auto parts = shard(lens.data(), n_frames, nd);
     std::vector<int> rcs(nd, 0);
     if (nd == 1) {
-        rcs[0] = decompress_on_device(*ctx->devs[0], frames, parts[0].data(), n_frames, payloads, payload_bytes,
-                                      out_samples, out_dev);
+        rcs[0] = decompress_on_device(*D0, frames, parts[0].data(), n_frames, payloads, payload_bytes, out_samples, out_dev);
+        if (rcs[0]) {
+            ctx->err = D0->err;
+            return rcs[0];
+        }
+        return ATSC_OK;
     } else {
         std::vector<std::thread> th;
         for (size_t d = 0; d < nd; d++)

@@ -12,6 +12,8 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <memory>
+#include <new>
 #include <vector>
 
 #include "../../include/atsc_gpu.h"
@@ -120,15 +122,30 @@ extern "C" int atsc_gpu_compress_series(atsc_ctx *ctx, const double *samples, co
                        compressor == ATSC_AUTO;
     const float max_error = (float)error_pct / 100.0f;  // `arguments.error as f32 / 100.0`
     std::vector<atsc_frame_out> fo(nf);
-    uint64_t pcap = 0;
-    for (uint32_t i = 0; i < nf; i++) pcap += (uint64_t)f_len[i] * 16 + 64;  // worst case: RLE of all-distinct f64
-    std::vector<uint8_t> payload(pcap);
+    // Payload staging: uninitialised, ~2 B per sample to start with (real fleets need about 1); the call reports
+    // the size it needed when that is not enough (ATSC_ERR_CAPACITY + payload_used) and is repeated once with it.
+    // The worst case is 16 B per sample (RLE of all-distinct f64): sizing -- and zero-filling -- for it up front
+    // cost 8 GiB of host memory per 256 Mi-sample batch.
+    uint64_t total_len = 0;
+    for (uint32_t i = 0; i < nf; i++) total_len += f_len[i];
+    uint64_t pcap = total_len * 2 + 64 * (uint64_t)nf + 4096;
+    std::unique_ptr<uint8_t[]> payload_mem;
     uint64_t pused = 0;
     if (nf) {
-        int rc = atsc_gpu_compress_frames(ctx, base, f_off.data(), f_len.data(), nf, compressor, max_error, speed,
-                                          lossy ? 1 : 0, fo.data(), payload.data(), pcap, &pused);
-        if (rc) return rc;
+        for (int attempt = 0;; attempt++) {
+            payload_mem.reset(new (std::nothrow) uint8_t[pcap]);
+            if (!payload_mem) return ATSC_ERR_CAPACITY;
+            int rc = atsc_gpu_compress_frames(ctx, base, f_off.data(), f_len.data(), nf, compressor, max_error, speed,
+                                              lossy ? 1 : 0, fo.data(), payload_mem.get(), pcap, &pused);
+            if (rc == ATSC_ERR_CAPACITY && attempt == 0 && pused > pcap) {
+                pcap = pused + 64;
+                continue;
+            }
+            if (rc) return rc;
+            break;
+        }
     }
+    const uint8_t *payload = payload_mem.get();
     // ---- CompressedStream::to_bytes per series
     uint64_t w = 0;
     bool overflow = false;
@@ -156,7 +173,7 @@ extern "C" int atsc_gpu_compress_series(atsc_ctx *ctx, const double *samples, co
             put_varint(hdr, fo[i].compressor);
             put_varint(hdr, fo[i].payload_len);
             emit(hdr.data(), hdr.size());
-            emit(payload.data() + fo[i].payload_off, fo[i].payload_len);
+            emit(payload + fo[i].payload_off, fo[i].payload_len);
             tie |= fo[i].near_tie;
         }
         bro_off[s] = start;

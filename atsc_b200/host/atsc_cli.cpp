@@ -16,6 +16,8 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <memory>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -175,6 +177,53 @@ int process_directory(atsc_ctx *ctx, const Args &a) {
     int ret = 0;
     const uint64_t BATCH_SAMPLES = 256ull << 20;
     const size_t BATCH_FILES = 4096;
+    // One GPU call expands the series [s0, s1) of a batch.  When the call fails (one malformed or truncated
+    // .bro fails the whole call) the batch falls back to one call per file, so every healthy file is still
+    // written and the offending path is named -- the reference works per file and carries on (main.rs:50-68).
+    auto expand = [&](const std::vector<uint8_t> &blob, const std::vector<uint64_t> &off, const std::vector<uint64_t> &len,
+                      const std::vector<std::string> &names, uint32_t s0, uint32_t s1, auto &&self) -> void {
+        const uint32_t n = s1 - s0;
+        std::vector<uint64_t> count(n), ooff(n);
+        int rc = atsc_gpu_decompress_series(ctx, blob.data(), off.data() + s0, len.data() + s0, n, nullptr, nullptr, count.data());
+        uint64_t total = 0;
+        for (uint32_t s = 0; s < n; s++) {
+            ooff[s] = total;
+            total += count[s];
+        }
+        std::vector<double> out;
+        if (!rc) {
+            // a hostile header can claim 131072 samples per 8-byte Constant frame: refuse absurd totals, survive bad_alloc
+            uint64_t bytes_in = 0;
+            for (uint32_t s = 0; s < n; s++) bytes_in += len[s0 + s];
+            if (total > (1ull << 34) || total / 131072 > bytes_in) {
+                rc = ATSC_ERR_FORMAT;
+            } else {
+                try {
+                    out.resize((size_t)total + 1);
+                } catch (const std::bad_alloc &) {
+                    rc = ATSC_ERR_CAPACITY;
+                }
+            }
+        }
+        if (!rc && total)
+            rc = atsc_gpu_decompress_series(ctx, blob.data(), off.data() + s0, len.data() + s0, n, out.data(), ooff.data(), count.data());
+        if (rc) {
+            if (n == 1) {
+                fprintf(stderr, "decompress failed (%d): %s File: %s\n", rc, atsc_gpu_last_error(ctx), names[s0].c_str());
+                ret = 1;
+            } else {
+                for (uint32_t s = s0; s < s1; s++) self(blob, off, len, names, s, s + 1, self);
+            }
+            return;
+        }
+        for (uint32_t s = 0; s < n; s++) {
+            const double *p = out.data() + ooff[s];
+            if (a.verbose) print_vec("Output", std::vector<double>(p, p + count[s]));
+            std::vector<uint8_t> w(atsc_wbro_encode(p, count[s], nullptr, 0));
+            atsc_wbro_encode(p, count[s], w.data(), w.size());
+            if (!write_file(with_extension(names[s0 + s], "wbro"), w.data(), w.size())) ret = 1;
+        }
+    };
     if (a.uncompress) {
         size_t i = 0;
         while (i < files.size()) {
@@ -199,33 +248,46 @@ int process_directory(atsc_ctx *ctx, const Args &a) {
                 names.push_back(path);
                 blob.insert(blob.end(), file.begin(), file.end());
             }
-            const uint32_t n = (uint32_t)names.size();
-            if (!n) continue;
-            std::vector<uint64_t> count(n), ooff(n);
-            int rc = atsc_gpu_decompress_series(ctx, blob.data(), off.data(), len.data(), n, nullptr, nullptr, count.data());
-            uint64_t total = 0;
-            for (uint32_t s = 0; s < n; s++) {
-                ooff[s] = total;
-                total += count[s];
-            }
-            std::vector<double> out((size_t)total + 1);
-            if (!rc && total)
-                rc = atsc_gpu_decompress_series(ctx, blob.data(), off.data(), len.data(), n, out.data(), ooff.data(), count.data());
-            if (rc) {
-                fprintf(stderr, "decompress failed (%d): %s\n", rc, atsc_gpu_last_error(ctx));
-                ret = 1;
-                continue;
-            }
-            for (uint32_t s = 0; s < n; s++) {
-                const double *p = out.data() + ooff[s];
-                if (a.verbose) print_vec("Output", std::vector<double>(p, p + count[s]));
-                std::vector<uint8_t> w(atsc_wbro_encode(p, count[s], nullptr, 0));
-                atsc_wbro_encode(p, count[s], w.data(), w.size());
-                if (!write_file(with_extension(names[s], "wbro"), w.data(), w.size())) ret = 1;
-            }
+            if (!names.empty()) expand(blob, off, len, names, 0, (uint32_t)names.size(), expand);
         }
         return ret;
     }
+    // the same for compression: series [s0, s1) of a batch in one call, per file when that fails.  The
+    // output buffer starts at ~2 B/sample and grows on ATSC_ERR_CAPACITY (worst case 16 B/sample).
+    auto squeeze = [&](const std::vector<double> &samples, const std::vector<uint64_t> &off, const std::vector<uint64_t> &len,
+                       const std::vector<std::string> &names, uint32_t s0, uint32_t s1, auto &&self) -> void {
+        const uint32_t n = s1 - s0;
+        uint64_t ns = 0;
+        for (uint32_t s = s0; s < s1; s++) ns += len[s];
+        std::vector<uint64_t> boff(n), blen(n);
+        std::unique_ptr<uint8_t[]> bro;
+        const uint64_t worst = ns * 16 + 4096 * (uint64_t)n + 64 * (ns / 512 + 8 * (uint64_t)n);
+        uint64_t cap = std::min<uint64_t>(worst, ns * 2 + 4096 * (uint64_t)n + (1u << 20));
+        double dummy = 0.0;
+        int rc;
+        for (;;) {
+            bro.reset(new (std::nothrow) uint8_t[cap]);
+            if (!bro) {
+                rc = ATSC_ERR_CAPACITY;
+                break;
+            }
+            rc = atsc_gpu_compress_series(ctx, samples.empty() ? &dummy : samples.data(), off.data() + s0, len.data() + s0, n,
+                                          (uint8_t)a.compressor, a.error, a.speed, bro.get(), cap, boff.data(), blen.data(), nullptr);
+            if (rc != ATSC_ERR_CAPACITY || cap >= worst) break;
+            cap = std::min<uint64_t>(worst, cap * 4);
+        }
+        if (rc) {
+            if (n == 1) {
+                fprintf(stderr, "compress failed (%d): %s File: %s\n", rc, atsc_gpu_last_error(ctx), names[s0].c_str());
+                ret = 1;
+            } else {
+                for (uint32_t s = s0; s < s1; s++) self(samples, off, len, names, s, s + 1, self);
+            }
+            return;
+        }
+        for (uint32_t s = 0; s < n; s++)
+            if (!write_file(with_extension(names[s0 + s], "bro"), bro.get() + boff[s], (size_t)blen[s])) ret = 1;
+    };
     size_t i = 0;
     while (i < files.size()) {
         std::vector<double> samples;
@@ -244,21 +306,7 @@ int process_directory(atsc_ctx *ctx, const Args &a) {
             names.push_back(path);
             samples.insert(samples.end(), data.begin(), data.end());
         }
-        const uint32_t n = (uint32_t)names.size();
-        if (!n) continue;
-        std::vector<uint8_t> bro(samples.size() * 16 + 4096 * (size_t)n + 64 * (samples.size() / 512 + 8 * (size_t)n));
-        std::vector<uint64_t> boff(n), blen(n);
-        double dummy = 0.0;
-        int rc = atsc_gpu_compress_series(ctx, samples.empty() ? &dummy : samples.data(), off.data(), len.data(), n,
-                                          (uint8_t)a.compressor, a.error, a.speed, bro.data(), bro.size(), boff.data(),
-                                          blen.data(), nullptr);
-        if (rc) {
-            fprintf(stderr, "compress failed (%d): %s\n", rc, atsc_gpu_last_error(ctx));
-            ret = 1;
-            continue;
-        }
-        for (uint32_t s = 0; s < n; s++)
-            if (!write_file(with_extension(names[s], "bro"), bro.data() + boff[s], (size_t)blen[s])) ret = 1;
+        if (!names.empty()) squeeze(samples, off, len, names, 0, (uint32_t)names.size(), squeeze);
     }
     return ret;
 }

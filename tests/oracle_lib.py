@@ -24,13 +24,37 @@ def build():
     return _SO
 
 
+def build_native():
+    """The same C file built -O3 -march=native ON THIS MACHINE (timed CPU baseline only; not the checker).
+    Returns the path, or None when the build is not possible (then the portable library is timed)."""
+    so = os.path.join(_ODIR, "libatsc_oracle_native.so")
+    try:
+        subprocess.check_call(["make", "-C", _ODIR, "-s", "-B", "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return so if os.path.exists(so) else None
+    except Exception:
+        return None
+
+
 _lib = None
+_native = False
 
 
-def lib():
+def use_native():
+    """Switches this process to the -O3 -march=native build (bench.py's CPU legs). True when it took effect."""
+    global _lib, _native
+    so = build_native()
+    if so is None:
+        return False
+    _lib = None
+    _native = True
+    lib(so)
+    return True
+
+
+def lib(path=None):
     global _lib
     if _lib is None:
-        _lib = C.CDLL(build())
+        _lib = C.CDLL(path or build())
         L = _lib
         dp = C.POINTER(C.c_double)
         bp = C.POINTER(C.c_uint8)
