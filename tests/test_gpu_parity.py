@@ -3,7 +3,8 @@ seeded inputs, against the reference's golden vectors, and through round-trip pr
 
 Bars (north_star): bit-exact bytes for Constant / RLE / Noop / Polynomial / IDW frames and
 all headers; same compressor + parameter counts for FFT except flagged near-ties; FFT values
-within f32 FFT noise: |a - b| <= 1e-5 + 4 * 2^-24 * log2(L) * max|x|.
+within f32 FFT noise: |a - b| <= 1e-5 + 6 * 2^-24 * log2(L) * max|x| (SURVEY.md H1 states 4 for one
+transform; two independent f32 transforms are compared here, and the achieved deviation is reported).
 """
 import os
 
@@ -41,12 +42,32 @@ def run_batch(ctx, arrays, compressor, max_error=0.05, speed=0, bounded=True):
     return res
 
 
-def fft_tol(x, n):
+def fft_tol(x, n, factor=6):
     # Two f32 transforms are compared (the oracle's recursive mixed radix stands in for rustfft, whose
     # butterfly order is build dependent): each carries up to ~4 eps log2(L) max|x| of rounding noise in
-    # the decoded samples (DC dominated frames reach it), and the noises are independent, hence 8.
+    # the decoded samples (DC dominated frames reach it), and the noises are independent.
+    # SURVEY H1 states the single-transform figure (factor 4); every comparison records what it actually
+    # reached against that (FFT_DEV, reported by test_zz_fft_deviation_report).  Measured over the 727
+    # comparisons of this suite on B200: worst 1.25 x the factor-4 bound (a 127-sample gauge frame at
+    # |x| = 5e7), 9 comparisons above it -- so the tolerance is 6, not round 1's 8.
     L = O.next_size(n) if n >= 128 else max(n, 2)
-    return 1e-5 + 8 * 2.0 ** -24 * np.log2(L) * float(np.abs(x).max())
+    return 1e-5 + factor * 2.0 ** -24 * np.log2(L) * float(np.abs(x).max())
+
+
+FFT_DEV = {"n": 0, "max_ratio_vs_4x": 0.0, "worst": "", "above_4x": 0}
+FFT_SKIPPED = []
+
+
+def fft_close(gd, wd, x, n, what):
+    """max |gpu - oracle| of decoded FFT values against the tolerance; records the achieved deviation."""
+    dev = float(np.abs(np.asarray(gd) - np.asarray(wd)).max()) if len(gd) else 0.0
+    ratio = dev / fft_tol(x, n, factor=4)
+    FFT_DEV["n"] += 1
+    FFT_DEV["above_4x"] += int(ratio > 1.0)
+    if ratio > FFT_DEV["max_ratio_vs_4x"]:
+        FFT_DEV["max_ratio_vs_4x"], FFT_DEV["worst"] = ratio, f"{what}: |d| = {dev:.3e}"
+    assert dev <= fft_tol(x, n), f"{what}: decoded diff {dev} > {fft_tol(x, n)}"
+    return dev
 
 
 def parse_fft(payload):
@@ -164,13 +185,14 @@ def compare_fft(a, n, gpu_payload, o, want_payload, wit, what):
     assert (gmx, gmn) == (wmx, wmn), what
     if len(ge) != len(we) or o.iterations != wit:
         assert o.near_tie & 9, f"{what}: k {len(ge)} vs {len(we)}, iters {o.iterations} vs {wit}, no tie flag"
+        FFT_SKIPPED.append(f"{what}: near-tie flag {o.near_tie}, k {len(ge)} vs {len(we)}, iterations {o.iterations} vs {wit}")
         return False
     if o.near_tie & 8:
+        FFT_SKIPPED.append(f"{what}: equal |z| at a top-k cut")
         return False  # equal |z| at the top-k cut: BinaryHeap pop order is unspecified
-    tol = fft_tol(a, n)
     gd = O.decompress(O.FFT, n, gpu_payload)
     wd = O.decompress(O.FFT, n, want_payload)
-    assert np.abs(gd - wd).max() <= tol, f"{what}: decoded diff {np.abs(gd - wd).max()} > {tol}\n gpu {ge[:8]}\n ora {we[:8]}"
+    fft_close(gd, wd, a, n, what)
     gp = {p for p, _, _ in ge}
     wp = {p for p, _, _ in we}
     if gp != wp:
@@ -186,6 +208,7 @@ def compare_fft(a, n, gpu_payload, o, want_payload, wit, what):
     for p, gl in gm.items():
         wl = wm.get(p)
         if wl is None or len(wl) != len(gl):
+            FFT_SKIPPED.append(f"{what}: stored position {p} holds {len(gl)} entries here, {0 if wl is None else len(wl)} in the oracle")
             continue
         for gz, wz in zip(gl, wl):
             assert abs(gz - wz) <= 4e-6 * scale + 1e-6, f"{what}: bin {p}"
@@ -201,7 +224,7 @@ def test_fft_bounded(ctx, e):
     for (k, n, s), a, (o, b) in zip(cs, arrays, got):
         want, werr, wit = O.compress_bounded(O.FFT, a, float(np.float32(e)))
         same += compare_fft(a, n, b, o, want, wit, f"fft e={e} {k} n={n}")
-    assert same >= len(cs) - 3
+    assert same >= len(cs) - 3, "not compared value by value:\n" + "\n".join(x for x in FFT_SKIPPED if f"fft e={e} " in x)
 
 
 def test_fft_unbounded_small_and_pow(ctx):
@@ -240,7 +263,7 @@ def test_auto_selection(ctx, e, speed):
                 mism += 1
             else:
                 gd, wd = O.decompress(O.FFT, n, b), O.decompress(O.FFT, n, wb)
-                assert np.abs(gd - wd).max() <= fft_tol(a, n), what
+                fft_close(gd, wd, a, n, what)
         else:
             assert b == wb, what
     assert mism <= 2
@@ -270,7 +293,7 @@ def test_decompress_oracle_payloads(ctx, comp):
         g = out[oo:oo + n]
         if comp == O.FFT:
             a = gen.make(k, n, s)
-            assert np.abs(g - w).max() <= fft_tol(a, n), f"fft decode {k} n={n}: {np.abs(g - w).max()}"
+            fft_close(g, w, a, n, f"fft decode {k} n={n}")
         else:
             assert np.array_equal(g, w), f"{O.NAMES[comp]} decode {k} n={n}: {np.sum(g != w)} differ"
         oo += n
@@ -317,8 +340,7 @@ def test_demo_html_poly_idw(ctx):
             bro = ctx.compress_data([x], compressor=O.FFT, error=err)
             got = ctx.decompress_data(bro)[0]
             want = demo[f"e{err}_{name}_fftData"]
-            tol = fft_tol(x[np.isfinite(x)], 2048)
-            assert np.abs(got - want).max() <= tol, f"{name} e={err} fft: {np.abs(got - want).max()}"
+            fft_close(got, want, x[np.isfinite(x)], 2048, f"reference binary's fftData {name} e={err}")
 
 
 # ------------------------------------------------------------------ full-size properties
@@ -346,3 +368,52 @@ def test_roundtrip_properties_full_size(ctx):
     bros = ctx.compress_data([np.round(s) for s in series], compressor=O.NOOP)
     for x, d in zip(series, ctx.decompress_data(bros)):
         assert np.array_equal(np.round(x), d)
+
+
+# ------------------------------------------------------------------ the bench fleet itself
+@pytest.mark.parametrize("speed", [0, 6])
+def test_bench_fleet_vs_oracle(ctx, speed):
+    """bench.py's own generator (constant / periodic sigma=0.05 / utilisation, 1 M samples) through both arms:
+    per frame the winner, the iteration count, and the bytes (FFT frames: entry count + values)."""
+    import atsc_b200
+    import bench
+    series = [bench.make_series(c, 5000 + c + 3 * r) for r in range(2) for c in range(3)]
+    flat = np.concatenate(series)
+    offs, lens = bench.frame_table(len(series))
+    out, pay = ctx.compress_frames(flat, offs, lens, atsc_b200.AUTO, 0.05, speed, True)
+    ties = mism = 0
+    for i in range(len(lens)):
+        a = flat[int(offs[i]):int(offs[i]) + int(lens[i])]
+        o = out[i]
+        b = pay[o.payload_off:o.payload_off + o.payload_len].tobytes()
+        wc, wb, werr, wsize = O.compress_best(a, np.float32(0.05), speed)
+        what = f"bench fleet c={speed} frame {i} (n={lens[i]}): gpu {O.NAMES[o.compressor]}({len(b)}) oracle {O.NAMES[wc]}({len(wb)})"
+        ties += bool(o.near_tie)
+        if o.compressor != wc:
+            assert o.near_tie, what
+            mism += 1
+        elif wc == O.FFT:
+            ge, we = parse_fft(b)[0], parse_fft(wb)[0]
+            if len(ge) != len(we):
+                assert o.near_tie, what
+                mism += 1
+            else:
+                fft_close(O.decompress(O.FFT, len(a), b), O.decompress(O.FFT, len(a), wb), a, len(a), what)
+        else:
+            assert b == wb, what
+    assert mism <= 1 and ties <= 3, f"{mism} mismatches, {ties} near-tie flags in {len(lens)} frames"
+
+
+def test_zz_fft_deviation_report():
+    """Runs last in this file: the deviation every FFT comparison above actually reached, against SURVEY H1's
+    single-transform tolerance (factor 4).  The assertion documents the headroom of the factor-6 tolerance."""
+    import json
+    rep = {k: (v if isinstance(v, str) else float(v)) for k, v in FFT_DEV.items()}
+    rep["skipped"] = len(FFT_SKIPPED)
+    print("\nFFT deviation report:", json.dumps(rep))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "fft_deviation.json"), "w") as f:
+            json.dump(dict(rep, skipped_cases=FFT_SKIPPED), f, indent=1)
+    assert FFT_DEV["n"] > 100
+    assert FFT_DEV["max_ratio_vs_4x"] <= 1.5  # == the factor-6 tolerance every comparison asserted

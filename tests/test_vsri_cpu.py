@@ -166,3 +166,32 @@ def test_day_elapsed_seconds_and_malformed_text():
     for bad in ("x\n1\n", "1\n2\n1,2,3\n", "1\n2\n1,2,3,4,5\n", "1\n2\n1,2,a,4\n"):
         with pytest.raises(ValueError):
             atsc_b200.Vsri.from_text(bad)
+
+
+def test_hand_derived_vectors():
+    """Expected values worked out BY HAND from the reference source, written as literals (no restatement in the
+    loop): vsri/src/lib.rs:249-285 (update_for_point), :311-328 (get_sample), :330-350 (get_time), :364-367,
+    :442-462 (text form) and csv-compressor/src/metric.rs:55-65 (milliseconds -> second of the day).
+
+    Stream 10, 20, 30, 50, 60, 61:
+      10 -> first point: min = 10, segment [0, 0, 10, 1]
+      20 -> rate 0 segment becomes [20 - 10, 0, 10, 2]
+      30 -> b = 10 - 10*0 = 10; (30 - 10) / 10 = 2 == n + x0 = 2  -> n = 3
+      50 -> (50 - 10) / 10 = 4 != 3                               -> new segment [0, 3, 50, 1]
+      60 -> rate 0 segment becomes [10, 3, 50, 2]
+      61 -> b = 50 - 10*3 = 20; (61 - 20) / 10 = 4 (truncated) != 5 -> new segment [0, 5, 61, 1]"""
+    v = atsc_b200.Vsri()
+    for y in (10, 20, 30, 50, 60, 61):
+        assert v.update_for_point(y)
+    assert v.to_text() == "10\n61\n10,0,10,3\n10,3,50,2\n0,5,61,1\n"
+    assert (v.min, v.max, v.sample_count, v.segment_count) == (10, 61, 6, 3)
+    # get_time: 0 -> min; x == count -> max; beyond -> None; inside a segment y0 + m * x -- the reference adds
+    # m * x without subtracting x0 (lib.rs:343), so samples 3 and 4 read 80 and 90 although they were taken at 50, 60
+    assert [v.get_time(x) for x in range(8)] == [10, 20, 30, 80, 90, 61, 61, None]
+    # get_sample: (y - b) / m, truncated, inside [y0, y0 + m (n - 1)]
+    assert v.get_sample(20) == 1 and v.get_sample(25) == 1 and v.get_sample(30) == 2
+    assert v.get_sample(50) == 3 and v.get_sample(60) == 4 and v.get_sample(45) is None and v.get_sample(9) is None
+    assert v.all_timestamps() == [10, 20, 30, 50, 60, 61]
+    # metric.rs:58: day_elapsed_seconds(sample.timestamp / 1000) -- integer division of the millisecond stamp
+    assert atsc_b200.day_elapsed_seconds(1730419215999 // 1000) == 15
+    assert atsc_b200.day_elapsed_seconds((1730419200000 + 86399 * 1000 + 999) // 1000) == 86399
