@@ -6,7 +6,9 @@ constant/periodic/noisy") scaled to one GPU: S series x 1,000,000 samples per GP
 constant, one third periodic (SURVEY.md C2 formula, sigma 0.05), one third noisy (C3 class b
 utilisation gauge), `atsc --compressor auto -e 5 -c 0`; the 100k x 1M fleet of the config is
 800 GB and does not fit, so each GPU processes a stated subsample per step (weak scaling: the
-per-GPU share is fixed as N grows, frames never communicate, no collective).
+per-GPU share is fixed as N grows, frames never communicate, no collective).  The fleet is
+generated ON THE DEVICE (same formulas as tests/gen.py, torch RNG) so that a step can be large:
+1152 series = 9.2 GB per GPU, 16 waves of the library's pipeline.
 
 One "step" = one pass of the hot path over the GPU's whole batch:
   value   : Msamples/s, inputs resident in HBM when the clock starts, payloads + frame
@@ -14,8 +16,15 @@ One "step" = one pass of the hot path over the GPU's whole batch:
   e2e     : same call with the samples in pinned HOST memory (H2D inside the timed region).
   roofline: dominant kernel (largest summed CUDA-event time) -- algorithmic bytes = 8 B x samples of
             the frames it reads / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline: the oracle port (C restatement of the reference) on the host cores, bounded sample.
+  cpu_baseline: the oracle port (C restatement of the reference, rebuilt -O3 -march=native on this
+            machine) on the host cores, bounded sample.
   decompress: GB/s of f64 output for the BRO fleet produced by the compress step.
+  configs : (N = 1 only) the other named shapes of BASELINE.json -- FFT only on one 1 M-sample series,
+            Polynomial / IDW on 65,536-sample series, auto at -c 6, an all-noise fleet, decompression
+            of the polynomial fleet -- each with its throughput, fraction of the HBM line and the CPU
+            port beside it on a bounded sample.
+`--single-process`: ONE context sharding a call's frames over all visible GPUs (host buffers in,
+payload gathered to the host) instead of one process per GPU.
 """
 import argparse
 import json
@@ -34,6 +43,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 SERIES_LEN = 1_000_000
 ERROR_PCT = 5
 SPEED = 0
+DEFAULT_SERIES = 1152
 
 
 def make_series(cls, seed):
@@ -46,17 +56,45 @@ def make_series(cls, seed):
 
 
 def make_fleet(n_series, seed0, out):
-    """Fills out[n_series, SERIES_LEN] with the mixed fleet (class = series index mod 3)."""
+    """Fills out[n_series, SERIES_LEN] with the mixed fleet (class = series index mod 3); numpy, host."""
     for s in range(n_series):
         out[s, :] = make_series(s % 3, seed0 + s)
 
 
-def frame_table(n_series):
+def make_fleet_device(n_series, seed0, device, kinds=(0, 1, 2), n=SERIES_LEN):
+    """The same three classes generated on the GPU (torch RNG): constant (seed mod 1000), periodic
+    100 + 20 sin(2 pi i / 1440) + 5 sin(2 pi i / 97) + 0.05 N(0,1), utilisation clip(50 + 30 sin(2 pi i / 4320) +
+    AR(1; phi 0.9, sigma 2), 0.01, 100) rounded to 2 decimals (the AR(1) filter as a 256-tap convolution:
+    0.9^256 = 2e-12).  kinds: class of series s = kinds[s % len(kinds)]; 3 = positive white noise (gen.noisy)."""
+    import torch
+    out = torch.empty((n_series, n), dtype=torch.float64, device=device)
+    g = torch.Generator(device=device)
+    i = torch.arange(n, dtype=torch.float64, device=device)
+    per = 100.0 + 20.0 * torch.sin(2 * np.pi * i / 1440.0) + 5.0 * torch.sin(2 * np.pi * i / 97.0)
+    util = 50.0 + 30.0 * torch.sin(2 * np.pi * i / 4320.0)
+    taps = (0.9 ** torch.arange(255, -1, -1, dtype=torch.float64, device=device)).view(1, 1, -1)
+    for s in range(n_series):
+        cls = kinds[s % len(kinds)]
+        g.manual_seed(seed0 + s)
+        if cls == 0:
+            out[s].fill_(float((seed0 + s) % 1000))
+        elif cls == 1:
+            out[s] = per + 0.05 * torch.randn(n, generator=g, dtype=torch.float64, device=device)
+        elif cls == 2:
+            e = torch.randn(n + 255, generator=g, dtype=torch.float64, device=device) * (2.0 * np.sqrt(1 - 0.81))
+            ar = torch.nn.functional.conv1d(e.view(1, 1, -1), taps).view(-1)
+            out[s] = torch.round(torch.clamp(util + ar, 0.01, 100.0), decimals=2)
+        else:
+            out[s] = torch.round(1.0 + 99.0 * torch.rand(n, generator=g, dtype=torch.float64, device=device), decimals=3)
+    return out
+
+
+def frame_table(n_series, series_len=SERIES_LEN):
     import atsc_b200
-    cs = atsc_b200.chunk_sizes(SERIES_LEN)
+    cs = atsc_b200.chunk_sizes(series_len)
     offs, lens = [], []
     for s in range(n_series):
-        o = s * SERIES_LEN
+        o = s * series_len
         for c in cs:
             offs.append(o)
             lens.append(c)
@@ -65,8 +103,8 @@ def frame_table(n_series):
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region (NVML, a few hundred Hz; falls back
-    to polling nvidia-smi when the NVML binding is unavailable)."""
+    """SM clock + throttle reasons sampled DURING the timed region (NVML at 20 Hz -- a 500 Hz poller per
+    rank showed up in the 8-rank numbers of round 1; falls back to polling nvidia-smi)."""
 
     def __init__(self, gpu):
         self.gpu = gpu
@@ -103,7 +141,7 @@ class ClockSampler:
                 pass
             if self.stop:  # at least one sample, taken while the region is still open
                 break
-            time.sleep(0.002)
+            time.sleep(0.05)
 
     def _run_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -138,10 +176,71 @@ class ClockSampler:
                 "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
+def bind_cores(local, world):
+    """Each rank on the cores `nvidia-smi topo -m` lists as its GPU's CPU affinity, split among the ranks that
+    share them (8 ranks on one socket contended for the same cores in round 1).  Best effort."""
+    try:
+        rows = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout.splitlines()
+        hdr = next(r for r in rows if "CPU Affinity" in r)
+        col = hdr.split("\t").index("CPU Affinity") if "\t" in hdr else None
+        sets = {}
+        for r in rows:
+            if r.startswith("GPU") and col is not None:
+                cells = r.split("\t")
+                gi = int(cells[0].strip()[3:])
+                cores = set()
+                for part in cells[col].strip().split(","):
+                    if "-" in part:
+                        a, b = part.split("-")
+                        cores.update(range(int(a), int(b) + 1))
+                    elif part.strip().isdigit():
+                        cores.add(int(part))
+                sets[gi] = cores
+        mine = sorted(sets[local] & os.sched_getaffinity(0))
+        sharers = sorted(g for g in sets if g < world and sets[g] == sets[local])
+        k = sharers.index(local)
+        share = mine[k * len(mine) // len(sharers):(k + 1) * len(mine) // len(sharers)]
+        if len(share) >= 2:
+            os.sched_setaffinity(0, share)
+            return f"{share[0]}-{share[-1]} ({len(share)} cores)"
+    except Exception:
+        pass
+    return None
+
+
+_native = None
+
+
+def oracle():
+    """The oracle library for the TIMED CPU legs: rebuilt -O3 -march=native on this machine when possible."""
+    global _native
+    import oracle_lib as O
+    if _native is None:
+        _native = O.use_native()
+        if not _native:
+            O.lib()
+    return O, ("-O3 -march=native build of oracle/atsc_oracle.c" if _native else "portable -O2 build of oracle/atsc_oracle.c")
+
+
+def cpu_port_rate(arr2d, compressor, error_pct, speed, threads, budget_s=6.0):
+    """Msamples/s of the CPU port on a small sample (rows = series), best of up to 3."""
+    O, how = oracle()
+    n, sl = arr2d.shape
+    t0 = time.perf_counter()
+    O.compress_batch(arr2d, compressor, error_pct, speed, threads)
+    dt = time.perf_counter() - t0
+    reps = 1
+    while dt * (reps + 1) / reps < budget_s and reps < 3:
+        t1 = time.perf_counter()
+        O.compress_batch(arr2d, compressor, error_pct, speed, threads)
+        dt = min(dt, time.perf_counter() - t1)
+        reps += 1
+    return n * sl / dt / 1e6
+
+
 def cpu_baseline(threads, budget_s=20.0):
     """Oracle port timed on the host cores on a bounded sample of the same workload."""
-    import oracle_lib as O
-    O.lib()
+    O, how = oracle()
     per_class = 4 * max(1, threads // 3)
     n = per_class * 3
     arr = np.empty((n, SERIES_LEN))
@@ -158,7 +257,7 @@ def cpu_baseline(threads, budget_s=20.0):
         reps += 1
     return {"value": n * SERIES_LEN / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
             "sample": f"{n} series x {SERIES_LEN} samples ({per_class} per class), best of {reps}, "
-                      f"{threads} threads, one series per thread at a time (reference is single-threaded per series)"}
+                      f"{threads} threads, one series per thread at a time (reference is single-threaded per series); {how}"}
 
 
 def run_reference(args):
@@ -167,8 +266,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import oracle_lib as O
-    O.lib()
+    O, how = oracle()
     threads = os.cpu_count() or 1
     per_class = 4 * max(1, threads // 3)
     n = per_class * 3
@@ -181,7 +279,7 @@ def run_reference(args):
         O.compress_batch(arr, O.AUTO, ERROR_PCT, SPEED, threads)
     dt = time.perf_counter() - t0
     v = args.steps * n * SERIES_LEN / dt / 1e6
-    sample = f"{n} series x {SERIES_LEN} samples per step ({per_class} per class), {threads} threads"
+    sample = f"{n} series x {SERIES_LEN} samples per step ({per_class} per class), {threads} threads; {how}"
     line = {
         "impl": "reference", "metric": "auto_compress_msamples_per_s", "value": v, "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -205,14 +303,157 @@ def workload_config(series_per_gpu, n_gpus):
     }
 
 
+def extra_configs(ctx, torch, dev_index, peak, threads, host_threads_note):
+    """The other named shapes of BASELINE.json (N = 1): throughput through the same C ABI with device-resident
+    inputs, fraction of the HBM line (8 B per sample), the CPU port on a bounded sample beside it."""
+    import atsc_b200
+    A = atsc_b200
+    device = torch.device("cuda", dev_index)
+    pbuf = np.empty(512 << 20, dtype=np.uint8)
+    res = {}
+
+    def run(name, fleet, comp, err, speed, reps, cpu_rows, cpu_comp=None, note=""):
+        S, n = fleet.shape
+        offs, lens = frame_table(S, n)
+        call = lambda: ctx.compress_frames(None, offs, lens, comp, err / 100.0, speed, True,  # noqa: E731
+                                           samples_ptr=fleet.data_ptr(), payload_out=pbuf)
+        for _ in range(2):
+            out, pay = call()
+        ctx.kernel_ms(reset=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        span = 0.0
+        for _ in range(reps):
+            out, pay = call()
+            span += ctx.last_call_ms
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        k = {a: round(b / reps, 4) for a, b in ctx.kernel_ms(reset=True).items() if b and not a.startswith("reserved")}
+        comps = np.array([out[i].compressor for i in range(len(lens))])
+        host = fleet[:cpu_rows].cpu().numpy()
+        cpu = cpu_port_rate(host, cpu_comp if cpu_comp is not None else comp, err, speed, min(threads, cpu_rows))
+        ms = dt / reps * 1e3
+        res[name] = {
+            "msamples_per_s": S * n / dt * reps / 1e6, "ms_per_call": ms, "device_ms_per_call": span / reps,
+            "samples_per_call": int(S * n), "frac_of_hbm_line": S * n * 8 / (dt / reps) / 1e9 / peak,
+            "winners": {A.COMPRESSOR_NAMES[c]: int((comps == c).sum()) for c in np.unique(comps)},
+            "compressed_bytes": int(len(pay)), "near_tie_frames": int(sum(1 for i in range(len(lens)) if out[i].near_tie)),
+            "kernel_ms_per_call": k,
+            "cpu_port_msamples_per_s": cpu, "cpu_sample": f"{cpu_rows} series x {n} samples, {min(threads, cpu_rows)} threads{host_threads_note}",
+            "note": note,
+        }
+        return out, pay, offs, lens
+
+    # C2: FFT compressor only, one synthetic 1 M-sample sinusoid + noise series (sigma 0.5), -e 1 / 5 / 10
+    import gen
+    c2 = torch.from_numpy(gen.periodic(SERIES_LEN, 42, sigma=0.5)).to(device).view(1, -1)
+    for e in (1, 5, 10):
+        run(f"C2_fft_1M_e{e}", c2, A.FFT, e, 0, 10, 1, note="one series: 11 frames, latency of the refinement loop, not throughput")
+    c2f = torch.from_numpy(np.stack([gen.periodic(SERIES_LEN, 42 + s, sigma=0.5) for s in range(48)])).to(device)
+    run("C2_fft_48x1M_e5", c2f, A.FFT, 5, 0, 5, min(threads, 16), note="the same class as a fleet: 48 series, FFT compressor only")
+    del c2f
+    # C3: Polynomial and IDW on 65,536-sample monitoring series (gauge walk / utilisation / sawtooth), -e 5
+    S3 = 3072
+    h3 = np.empty((S3, 65536))
+    for s in range(S3):
+        h3[s] = (gen.gauge_walk, gen.utilisation, gen.sawtooth)[s % 3](65536, 1000 + s)
+    c3 = torch.from_numpy(h3).to(device)
+    out3, pay3, offs3, lens3 = run("C3_polynomial_3072x64k", c3, A.POLYNOMIAL, 5, 0, 5, min(threads, 48) * 2,
+                                   note="subsample of the 10k x 64k fleet (3072 series, three classes)")
+    pay3 = pay3.copy()
+    run("C3_idw_96x64k", c3[:96], A.IDW, 5, 0, 3, max(3, min(threads, 12)), note="IDW is O(N K) per frame: 96 series")
+    # C5: decompression of the C3 polynomial fleet
+    frames_in = ctx.frames_in([(out3[i].compressor, int(lens3[i]), int(out3[i].payload_off), int(out3[i].payload_len), int(offs3[i]))
+                               for i in range(len(lens3))])
+    dout = torch.empty(S3 * 65536, dtype=torch.float64, device=device)
+    for _ in range(2):
+        ctx.decompress_frames(frames_in, pay3, out_ptr=dout.data_ptr())
+    ctx.kernel_ms(reset=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        ctx.decompress_frames(frames_in, pay3, out_ptr=dout.data_ptr())
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 10
+    dec_ms = ctx.kernel_ms(reset=True)["decode"] / 10
+    # CPU port: decompress 96 series of the same fleet
+    O, how = oracle()
+    bros = ctx.compress_data([h3[s] for s in range(96)], compressor=A.POLYNOMIAL, error=5)
+    boff = np.concatenate([[0], np.cumsum([len(b) for b in bros])]).astype(np.uint64)
+    blob = np.frombuffer(b"".join(bros), dtype=np.uint8).copy()
+    hout = np.empty((96, 65536))
+    import ctypes as C
+    t1 = time.perf_counter()
+    O.lib().atsc_oracle_decompress_batch(blob.ctypes.data_as(C.POINTER(C.c_uint8)), boff.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                         96, 65536, min(threads, 96), hout.ctypes.data_as(C.POINTER(C.c_double)))
+    cdt = time.perf_counter() - t1
+    res["C5_decompress_C3_polynomial"] = {
+        "gb_per_s_f64_out": S3 * 65536 * 8 / dt / 1e9, "ms_per_call": dt * 1e3, "kernel_gb_per_s": S3 * 65536 * 8 / (dec_ms * 1e-3) / 1e9,
+        "frac_of_hbm_line": S3 * 65536 * 8 / dt / 1e9 / peak, "payload_bytes": int(len(pay3)),
+        "cpu_port_gb_per_s": 96 * 65536 * 8 / cdt / 1e9, "cpu_sample": f"96 series x 65536 samples, {min(threads, 96)} threads",
+    }
+    del c3, dout
+    # C4 at -c 6 (sampled selection) and an all-noise fleet at -c 0
+    c4 = make_fleet_device(288, 5000, device)
+    run("C4_auto_c6_288x1M", c4, A.AUTO, 5, 6, 10, min(threads, 12), note="sampled selection: 128-sample probe frames pick the compressor")
+    del c4
+    noisy = make_fleet_device(24, 9000, device, kinds=(3,))
+    run("noisy_auto_c0_24x1M", noisy, A.AUTO, 5, 0, 3, min(threads, 12),
+        note="positive white noise: no candidate reaches 5 % cheaply, the FFT refinement loop runs all 23 iterations")
+    return res
+
+
+def run_single_process(args):
+    """One context over every visible GPU: frames sharded by the library, payload gathered to the host."""
+    import torch
+    import atsc_b200
+    import ctypes as C
+    n = min(args.gpus, torch.cuda.device_count()) if args.gpus > 1 else torch.cuda.device_count()
+    S = args.series * n
+    ctx = atsc_b200.Context(list(range(n)))
+    L = ctx.L
+    hptr = L.atsc_gpu_host_alloc(S * SERIES_LEN * 8)
+    host = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_double)), shape=(S, SERIES_LEN))
+    for g in range(n):
+        torch.cuda.set_device(g)
+        fl = make_fleet_device(args.series, 5000 + g * args.series, torch.device("cuda", g))
+        host[g * args.series:(g + 1) * args.series] = fl.cpu().numpy()
+        del fl
+    offs, lens = frame_table(S)
+    pcap = 256 << 20
+    pptr = L.atsc_gpu_host_alloc(pcap)
+    pbuf = np.ctypeslib.as_array(C.cast(pptr, C.POINTER(C.c_uint8)), shape=(pcap,))
+    call = lambda: ctx.compress_frames(host.reshape(-1), offs, lens, atsc_b200.AUTO, ERROR_PCT / 100.0, SPEED, True, payload_out=pbuf)  # noqa: E731
+    for _ in range(max(args.warmup, 2)):
+        out, pay = call()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out, pay = call()
+    dt = time.perf_counter() - t0
+    v = S * SERIES_LEN * args.steps / dt / 1e6
+    line = {"metric": "auto_compress_msamples_per_s", "value": v, "unit": "Msamples/s", "n_gpus": n, "steps": args.steps,
+            "warmup": max(args.warmup, 2), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "mode": "single-process: one atsc_ctx over all GPUs, host buffers in (H2D inside), payload gathered to the host",
+            "config": dict(workload_config(args.series, n), parallelism=f"one context sharding a call's frames over {n} GPU(s) by frame range"),
+            "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": S * SERIES_LEN * 8, "d2h_bytes_per_step": int(len(pay)) + len(lens) * 64},
+            "compressed_bytes": int(len(pay)), "gpu_launches": int(ctx.launches)}
+    print(json.dumps(line))
+    L.atsc_gpu_host_free(hptr)
+    L.atsc_gpu_host_free(pptr)
+    ctx.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--series", type=int, default=288, help="series per GPU (multiple of 3)")
+    ap.add_argument("--series", type=int, default=DEFAULT_SERIES, help="series per GPU (multiple of 3)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other named shapes (N = 1 runs them by default)")
+    ap.add_argument("--single-process", action="store_true")
     ap.add_argument("--as-rank", type=int, default=None, help="diagnostic: generate the fleet rank R of a multi-GPU run would get")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -224,10 +465,13 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    if args.single_process:
+        return run_single_process(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    cores = bind_cores(local, world) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its version banner to stdout when the first communicator is created: send fd 1 to
@@ -246,15 +490,16 @@ def main():
     S = args.series
     ctx = atsc_b200.Context([local])
     L = ctx.L
+    device = torch.device("cuda", local)
 
-    # ---- inputs: pinned host fleet (for e2e) + device copy (for value)
+    # ---- inputs: device fleet (for value) + pinned host copy (for e2e)
     nbytes = S * SERIES_LEN * 8
+    dev2d = make_fleet_device(S, 5000 + (rank if args.as_rank is None else args.as_rank) * S, device)
+    dev = dev2d.view(-1)
     hptr = L.atsc_gpu_host_alloc(nbytes)
     import ctypes as C
     host = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_double)), shape=(S, SERIES_LEN))
-    make_fleet(S, 5000 + (rank if args.as_rank is None else args.as_rank) * S, host)
-    dev = torch.empty(S * SERIES_LEN, dtype=torch.float64, device="cuda")
-    dev.copy_(torch.from_numpy(host.reshape(-1)))
+    torch.from_numpy(host).copy_(dev2d)
     torch.cuda.synchronize()
     offs, lens = frame_table(S)
     n_samples = S * SERIES_LEN
@@ -266,7 +511,7 @@ def main():
         torch.cuda.synchronize()
 
     # page-locked result buffer: payload bytes land in it straight from the device
-    pcap = 64 << 20
+    pcap = max(64 << 20, S * 80_000)
     pptr = L.atsc_gpu_host_alloc(pcap)
     pbuf = np.ctypeslib.as_array(C.cast(pptr, C.POINTER(C.c_uint8)), shape=(pcap,))
 
@@ -314,14 +559,15 @@ def main():
     value = world * n_samples * args.steps / dt / 1e6
 
     # ---- e2e: host buffers, H2D inside
-    for _ in range(2):
-        step_host()
-    dt_e2e, _ = timed(step_host, args.steps, "compress_e2e")
-    e2e_v = world * n_samples * args.steps / dt_e2e / 1e6
+    e2e_steps = max(3, min(args.steps, 10))
+    step_host()
+    dt_e2e, _ = timed(step_host, e2e_steps, "compress_e2e")
+    e2e_v = world * n_samples * e2e_steps / dt_e2e / 1e6
     d2h = int(len(payload)) + len(lens) * 168
 
     # ---- roofline of the dominant kernel
     comps = np.array([out[i].compressor for i in range(len(lens))])
+    near_ties = int(sum(1 for i in range(len(lens)) if out[i].near_tie))
     nonconst = comps != atsc_b200.CONSTANT
     fft_samples = int(lens[nonconst].astype(np.int64).sum())
     peaks = {}
@@ -330,9 +576,9 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    dom = max(("stats", "poly", "rle", "fft_fwd", "fft_small", "fft", "select", "emit"), key=lambda k: kms[k])  # host_issue is not a kernel
+    dom = max(("stats", "poly", "rle", "fft_fwd", "fft_small", "fft", "select", "emit", "front"), key=lambda k: kms[k])  # host_issue is not a kernel
     dom_ms = kms[dom] / args.steps
-    dom_samples = n_samples if dom in ("stats", "select") else fft_samples
+    dom_samples = n_samples if dom in ("stats", "select", "front") else fft_samples
     achieved = dom_samples * 8 / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     # the same kernels timed without other waves sharing the GPU (one engine): explains how much of
     # the in-pipeline duration above is contention
@@ -340,12 +586,13 @@ def main():
     try:
         os.environ["ATSC_ENGINES"] = "1"
         ctx1 = atsc_b200.Context([local])
+        offs1, lens1 = frame_table(288)
         for _ in range(2):
-            ctx1.compress_frames(None, offs, lens, atsc_b200.AUTO, ERROR_PCT / 100.0, SPEED, True,
+            ctx1.compress_frames(None, offs1, lens1, atsc_b200.AUTO, ERROR_PCT / 100.0, SPEED, True,
                                  samples_ptr=dev.data_ptr(), payload_out=pbuf)
         ctx1.kernel_ms(reset=True)
         for _ in range(3):
-            ctx1.compress_frames(None, offs, lens, atsc_b200.AUTO, ERROR_PCT / 100.0, SPEED, True,
+            ctx1.compress_frames(None, offs1, lens1, atsc_b200.AUTO, ERROR_PCT / 100.0, SPEED, True,
                                  samples_ptr=dev.data_ptr(), payload_out=pbuf)
         k1 = ctx1.kernel_ms(reset=True)
         ctx1.close()
@@ -366,46 +613,53 @@ def main():
             traffic_detail = dict(traffic_detail, algorithmic_bytes_of_that_launch=(96 if dom == "stats" else 64) * SERIES_LEN * 8)
     except Exception:
         pass
-    alg = {"stats": n_samples * 8, "poly": fft_samples * 8, "fft_fwd": fft_samples * 8}
+    alg1 = {"stats": 288 * SERIES_LEN * 8, "poly": 192 * SERIES_LEN * 8, "fft_fwd": 192 * SERIES_LEN * 8}
     one_engine = None
     if iso and "error" not in iso:
-        one_engine = {"k_" + k: {"ms_per_step": round(iso[k], 4), "achieved": alg[k] / (iso[k] * 1e-3) / 1e9,
-                                 "frac": alg[k] / (iso[k] * 1e-3) / 1e9 / peak}
-                      for k in alg if iso.get(k)}
+        one_engine = {"k_" + k: {"ms_per_288_series": round(iso[k], 4), "achieved": alg1[k] / (iso[k] * 1e-3) / 1e9,
+                                 "frac": alg1[k] / (iso[k] * 1e-3) / 1e9 / peak}
+                      for k in alg1 if iso.get(k)}
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_detail": traffic_detail, "one_engine": one_engine,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_step": dom_samples * 8,
                 "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items() if v and not k.startswith("reserved")},
-                "kernel_ms_per_step_one_engine": iso,
+                "kernel_ms_per_288_series_one_engine": iso,
                 "whole_step_frac": n_samples * 8 / (dt / args.steps) / 1e9 / peak,
                 "note": "achieved / frac / kernel_ms_per_step: CUDA events on each engine's stream inside the timed region "
                         "(waves of several engines overlap, so these durations include contention and add up to more "
-                        "than the step); one_engine: the same kernels with a single engine, i.e. each launch alone on "
-                        "the GPU, which is the figure to hold against the kernel's own roofline; k_poly and k_fft_fwd wait on "
-                        "loads (ncu long-scoreboard stalls), k_stats runs near the HBM line (DESIGN.md section 4); the HBM "
-                        "line is the task's stated denominator"}
+                        "than the step); one_engine: the same kernels on a 288-series call with a single engine, i.e. each "
+                        "launch alone on the GPU, which is the figure to hold against the kernel's own roofline; k_poly and "
+                        "k_fft_fwd wait on loads (ncu long-scoreboard stalls), k_stats runs near the HBM line (DESIGN.md "
+                        "section 4); the HBM line is the task's stated denominator"}
 
     # ---- decompression of the fleet just produced (device-resident output)
-    frames_in, po = [], 0
+    frames_in = []
     oo = 0
     for i in range(len(lens)):
         o = out[i]
         frames_in.append((o.compressor, int(lens[i]), int(o.payload_off), int(o.payload_len), oo))
         oo += int(lens[i])
     frames_in = ctx.frames_in(frames_in)
-    dout = torch.empty(n_samples, dtype=torch.float64, device="cuda")
+    # the payload stays page-locked (its H2D is inside the timed region): a second pinned buffer, because
+    # pbuf is reused by later compress calls
+    qptr = L.atsc_gpu_host_alloc(max(len(payload), 1))
+    qbuf = np.ctypeslib.as_array(C.cast(qptr, C.POINTER(C.c_uint8)), shape=(max(len(payload), 1),))
+    qbuf[:len(payload)] = payload
+    payload = qbuf[:len(payload)]
+    dout = dev  # the input fleet is no longer needed on the device: decode over it
+    dec_steps = max(3, min(args.steps, 10))
     for _ in range(2):
         ctx.decompress_frames(frames_in, payload, out_ptr=dout.data_ptr())
     ctx.kernel_ms(reset=True)
-    dt_dec, _ = timed(lambda: ctx.decompress_frames(frames_in, payload, out_ptr=dout.data_ptr()), args.steps, "decompress")
-    dec_ms = ctx.kernel_ms(reset=True)["decode"] / args.steps
+    dt_dec, _ = timed(lambda: ctx.decompress_frames(frames_in, payload, out_ptr=dout.data_ptr()), dec_steps, "decompress")
+    dec_ms = ctx.kernel_ms(reset=True)["decode"] / dec_steps
     hout = host.reshape(-1)  # page-locked; the input fleet is no longer needed
-    dt_dec_e2e, _ = timed(lambda: ctx.decompress_frames(frames_in, payload, out=hout), max(1, args.steps // 2))
-    dec = {"value": world * n_samples * 8 * args.steps / dt_dec / 1e9, "unit": "GB/s (f64 out)",
+    dt_dec_e2e, _ = timed(lambda: ctx.decompress_frames(frames_in, payload, out=hout), 3)
+    dec = {"value": world * n_samples * 8 * dec_steps / dt_dec / 1e9, "unit": "GB/s (f64 out)",
            "kernel_gbs": n_samples * 8 / (dec_ms * 1e-3) / 1e9 if dec_ms else None,
            "kernel_frac_of_hbm_peak": (n_samples * 8 / (dec_ms * 1e-3) / 1e9 / peak) if dec_ms else None,
-           "e2e_gbs": world * n_samples * 8 * max(1, args.steps // 2) / dt_dec_e2e / 1e9,
+           "e2e_gbs": world * n_samples * 8 * 3 / dt_dec_e2e / 1e9,
            "payload_bytes": int(len(payload))}
 
     # ---- sanity: the timed result is a real compress (sizes, winners)
@@ -414,24 +668,39 @@ def main():
 
     line = None
     if rank == 0:
+        threads = os.cpu_count() or 1
         cpu = None
+        configs = None
         if world == 1 and not args.no_cpu:
-            cpu = cpu_baseline(os.cpu_count() or 1)
+            cpu = cpu_baseline(threads)
+        if world == 1 and not args.no_configs:
+            L.atsc_gpu_host_free(hptr)
+            hptr = None
+            del dev2d, dev, dout
+            torch.cuda.empty_cache()
+            try:
+                configs = extra_configs(ctx, torch, local, peak, threads, "")
+            except Exception as ex:  # the headline must not die with an extra
+                configs = {"error": repr(ex)}
         line = {
             "metric": "auto_compress_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": dt / args.steps * 1e3,
-            "device_ms_per_step": dev_ms, "higher_is_better": True,
+            "device_ms_per_step": dev_ms, "host_issue_ms_per_step": kms["host_issue"] / args.steps, "cpu_binding": cores,
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32",
             "dtype_note": "f64 for stats / polynomial / rle / error metrics, f32 for the FFT (Complex<f32> in the reference)",
-            "data": "synthetic", "config": workload_config(S, world),
-            "e2e": {"value": e2e_v, "unit": "Msamples/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "decompress": dec,
-            "clocks": clk.summary(), "winners": hist, "compressed_bytes": int(len(payload)),
-            "compression_ratio": n_samples * 8 / max(1, len(payload)),
+            "data": "synthetic (generated on the device; same formulas as tests/gen.py)", "config": workload_config(S, world),
+            "e2e": {"value": e2e_v, "unit": "Msamples/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": launches, "near_tie_frames": near_ties, "frames_per_step": int(len(lens)),
+            "roofline": roofline, "cpu_baseline": cpu, "decompress": dec,
+            "clocks": clk.summary(), "winners": hist, "compressed_bytes": dec["payload_bytes"],
+            "compression_ratio": n_samples * 8 / max(1, dec["payload_bytes"]), "configs": configs,
         }
         print(json.dumps(line))
-    L.atsc_gpu_host_free(hptr)
+    if hptr is not None:
+        L.atsc_gpu_host_free(hptr)
     L.atsc_gpu_host_free(pptr)
+    L.atsc_gpu_host_free(qptr)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
