@@ -781,7 +781,15 @@ __device__ uint32_t dec_constant(const uint8_t *__restrict__ p, uint32_t len, ui
     double c = ds->dv[0];
     __syncthreads();
     if (bad) return 5;
-    for (uint32_t x = threadIdx.x; x < N; x += blockDim.x) out[x] = c;
+    // 16-byte stores over the aligned middle of the frame
+    const uint32_t head = (uint32_t)(((uintptr_t)out >> 3) & 1u) & (N ? 1u : 0u), pairs = (N - head) / 2u;
+    double2 *o2 = reinterpret_cast<double2 *>(out + head);
+    const double2 cc = make_double2(c, c);
+    for (uint32_t x = threadIdx.x; x < pairs; x += blockDim.x) o2[x] = cc;
+    if (threadIdx.x == 0) {
+        if (head) out[0] = c;
+        if (head + 2u * pairs < N) out[N - 1] = c;
+    }
     return 0;
 }
 

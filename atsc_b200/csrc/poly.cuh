@@ -275,8 +275,12 @@ __device__ inline void poly_expand(const double *__restrict__ pts_g, const PolyK
         __syncthreads();
     }
     auto pf = [&](uint32_t j) { return pts[j]; };
+    // |stored range| <= 1e10: wherever the clamp lets the quotient through, |n| <= 1e15 < 2^53 and the one-step
+    // form is the IEEE quotient (common.cuh: div_1e5_int53); beyond it the value is clamped away anyway
+    const bool small = fmax(fabs(vmin), fabs(vmax)) <= 1e10;
     auto fin = [&](double v) {
-        double o = div_1e5(round_half_away(__dmul_rn(v, 100000.0)));
+        const double n = round_half_away(__dmul_rn(v, 100000.0));
+        double o = small ? div_1e5_int53(n) : div_1e5(n);
         if (o < vmin) return vmin;
         if (o > vmax) return vmax;
         return o;
@@ -286,26 +290,58 @@ __device__ inline void poly_expand(const double *__restrict__ pts_g, const PolyK
         return;
     }
     const double stepd = (double)step;
-    for (uint32_t j = 1 + t; j + 1 < K; j += T) {
-        uint32_t pa = poly_pos(k, j - 1), pb = poly_pos(k, j + 1);
-        tang[j] = __dmul_rn(__ddiv_rn(__dsub_rn(pts[j + 1], pts[j - 1]), __dsub_rn((double)pb, (double)pa)), stepd);
-    }
-    __syncthreads();
     const uint32_t G = T / step, g = t / step, j = t - g * step;
+    double h00 = 0.0, h10 = 0.0, h01 = 0.0, h11 = 0.0;
     if (g < G) {
         const double tt = __ddiv_rn((double)j, stepd);
         const double two_t = __dmul_rn(tt, 2.0), three_t = __dmul_rn(tt, 3.0);
         const double t2 = __dmul_rn(tt, tt), t3 = __dmul_rn(t2, tt);
         const double two_t3 = __dmul_rn(t2, two_t), two_t2 = __dmul_rn(tt, two_t), three_t2 = __dmul_rn(tt, three_t);
-        const double h00 = __dadd_rn(__dsub_rn(two_t3, three_t2), 1.0), h10 = __dadd_rn(__dsub_rn(t3, two_t2), tt);
-        const double h01 = __dsub_rn(three_t2, two_t3), h11 = __dsub_rn(t3, t2);
-        // Catmull-Rom segments 1 .. K-3 (polynomial.rs:349): keys i and i+1 are regular
-#pragma unroll 2
-        for (uint32_t i = 1 + g; i + 3 <= K; i += G) {
-            const double av = pts[i], bv = pts[i + 1];
-            const double v = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(av, h00), __dmul_rn(tang[i], h10)), __dmul_rn(bv, h01)),
-                                       __dmul_rn(tang[i + 1], h11));
-            out[i * step + j] = fin(v);
+        h00 = __dadd_rn(__dsub_rn(two_t3, three_t2), 1.0);
+        h10 = __dadd_rn(__dsub_rn(t3, two_t2), tt);
+        h01 = __dsub_rn(three_t2, two_t3);
+        h11 = __dsub_rn(t3, t2);
+    }
+    // tangent at key jj from its neighbours' values (both neighbours regular except for the appended last key)
+    auto tangent = [&](uint32_t jj, double vm, double vp) {
+        const uint32_t pa = poly_pos(k, jj - 1), pb = poly_pos(k, jj + 1);
+        return __dmul_rn(__ddiv_rn(__dsub_rn(vp, vm), __dsub_rn((double)pb, (double)pa)), stepd);
+    };
+    if (smem && pts == pts_g && smem_cap >= 64u) {
+        // Many keys (small steps): the keys do not fit shared memory at once.  The frame is expanded in
+        // chunks of C segments whose keys and tangents are staged in shared memory, so that the inner loop
+        // reads them at shared-memory latency instead of from the L2-resident scratch.
+        const uint32_t C = (smem_cap - 8u) / 2u;  // segments per chunk
+        double *sp = smem, *st = smem + C + 4u;   // sp[q] = pts[c0 - 1 + q], st[q] = tangent of key c0 + q
+        for (uint32_t c0 = 1; c0 + 3 <= K; c0 += C) {
+            const uint32_t ns = min(C, K - 2u - c0);  // Catmull-Rom segments c0 .. c0 + ns - 1
+            __syncthreads();
+            for (uint32_t q = t; q < ns + 3u; q += T) sp[q] = pts_g[c0 - 1u + q];  // keys c0-1 .. c0+ns+1
+            __syncthreads();
+            for (uint32_t q = t; q <= ns; q += T) st[q] = tangent(c0 + q, sp[q], sp[q + 2u]);  // keys c0 .. c0+ns (<= K-2)
+            __syncthreads();
+            if (g < G) {
+#pragma unroll 4
+                for (uint32_t q = g; q < ns; q += G) {
+                    const double v = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sp[q + 1u], h00), __dmul_rn(st[q], h10)),
+                                                         __dmul_rn(sp[q + 2u], h01)),
+                                               __dmul_rn(st[q + 1u], h11));
+                    out[(c0 + q) * step + j] = fin(v);
+                }
+            }
+        }
+    } else {
+        for (uint32_t jj = 1 + t; jj + 1 < K; jj += T) tang[jj] = tangent(jj, pts[jj - 1], pts[jj + 1]);
+        __syncthreads();
+        if (g < G) {
+            // Catmull-Rom segments 1 .. K-3 (polynomial.rs:349): keys i and i+1 are regular
+#pragma unroll 4
+            for (uint32_t i = 1 + g; i + 3 <= K; i += G) {
+                const double av = pts[i], bv = pts[i + 1];
+                const double v = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(av, h00), __dmul_rn(tang[i], h10)), __dmul_rn(bv, h01)),
+                                           __dmul_rn(tang[i + 1], h11));
+                out[i * step + j] = fin(v);
+            }
         }
     }
     // the Linear ends: segment 0, segment K-2 (possibly irregular), the last sample
