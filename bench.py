@@ -602,7 +602,7 @@ def main():
     finally:
         os.environ.pop("ATSC_ENGINES", None)
     # dram__bytes_read + dram__bytes_write of one launch of the dominant kernel, from the committed
-    # ncu --set full capture (profiles/traffic.json): that launch is one 96-series wave, whose
+    # ncu --set full capture (profiles/traffic.json): that launch is one 72-series wave, whose
     # algorithmic bytes are stated beside it
     traffic, traffic_detail = None, None
     try:
@@ -610,7 +610,6 @@ def main():
         traffic_detail = tj.get("k_" + dom)
         if traffic_detail:
             traffic = traffic_detail["bytes_per_launch"]
-            traffic_detail = dict(traffic_detail, algorithmic_bytes_of_that_launch=(96 if dom == "stats" else 64) * SERIES_LEN * 8)
     except Exception:
         pass
     alg1 = {"stats": 288 * SERIES_LEN * 8, "poly": 192 * SERIES_LEN * 8, "fft_fwd": 192 * SERIES_LEN * 8}
