@@ -647,8 +647,8 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     }
     CK(cudaEventRecord(E.ev[11], st));
     if (any_large) {
-        D.launches += launch_fft(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_arena, E.d_spec_xd, E.d_spec_keys,
-                                 E.queues + 3, E.queues + 10, spec > 0, st);
+        launch_fft(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_arena, E.d_spec_xd, E.d_spec_keys, E.queues + 3, st);
+        D.launches++;
     }
     CK(cudaEventRecord(E.ev[3], st));
     // RLE last: its sort runs only for frames where a size lower bound still beats Polynomial and FFT

@@ -403,10 +403,10 @@ __device__ inline uint32_t fft_bin_of(uint32_t i, uint32_t pM, uint32_t pM1, uin
 // ---------------------------------------------------------------------------------------
 __device__ inline void find_digit(const uint32_t *hist, uint32_t nbins, uint32_t remaining, uint32_t *sh,
                                   uint32_t *d, uint32_t *above, uint32_t *cnt) {
-    const uint32_t t = threadIdx.x, per = nbins >= blockDim.x ? nbins / blockDim.x : 1;  // <= 16
-    uint32_t loc[16], sum = 0;
+    const uint32_t t = threadIdx.x, per = nbins >= blockDim.x ? nbins / blockDim.x : 1;  // <= 8
+    uint32_t loc[8], sum = 0;
 #pragma unroll
-    for (uint32_t j = 0; j < 16; j++) {
+    for (uint32_t j = 0; j < 8; j++) {
         uint32_t pos = t * per + j;  // position in descending-digit order
         loc[j] = (j < per && pos < nbins) ? hist[nbins - 1 - pos] : 0u;
         sum += loc[j];
@@ -416,7 +416,7 @@ __device__ inline void find_digit(const uint32_t *hist, uint32_t nbins, uint32_t
     if (excl < remaining && remaining <= excl + sum) {
         uint32_t acc = excl;
 #pragma unroll
-        for (uint32_t j = 0; j < 16; j++) {
+        for (uint32_t j = 0; j < 8; j++) {
             if (j < per && acc < remaining && remaining <= acc + loc[j]) {
                 sh[102] = nbins - 1 - (t * per + j);
                 sh[103] = acc;

@@ -374,8 +374,7 @@ __device__ void fft_frame(const double *__restrict__ d, FrameWork *fw, const Fft
 
 __global__ void __launch_bounds__(FFT_THREADS, 1) k_fft(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
                                                double max_err, const FftGeom *__restrict__ geoms, SlotPool pool,
-                                               FftEntry *arena, float2 *spec_xd, uint32_t *spec_keys, unsigned *q,
-                                               int which) {
+                                               FftEntry *arena, float2 *spec_xd, uint32_t *spec_keys, unsigned *q) {
     extern __shared__ float2 dyn_f2[];
     __shared__ double shd[64];
     __shared__ FftGeom sg;
@@ -386,9 +385,6 @@ __global__ void __launch_bounds__(FFT_THREADS, 1) k_fft(FrameWork *fr, uint32_t 
         if (i >= (int)n) break;
         FrameWork *fw = &fr[i];
         if (!fw->need_fft || fw->fft_valid == 2 || fw->fft_small) continue;  // 2: k_fft_fwd proved it cannot win
-        // which: 0 = every frame, 1 = frames whose spectrum k_fft_fwd left (fft2.cuh engine only: any CTA size),
-        //        2 = the others (fft.cuh engine: FFT_THREADS)
-        if (which && (which == 1) != (fw->fwd_done != 0)) continue;
         fft_frame(samples + fw->off, fw, geoms, ws, arena + fw->fft_list_off, max_err, dyn_f2, shd, &sg, spec_xd,
                   spec_keys);
     }
@@ -1153,23 +1149,10 @@ void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err
                 cudaStream_t st) {
     k_rle<<<grid_for(n, pool.rle_slots), BLOCK, RLE_HIST_WORDS * 4, st>>>(fr, n, samples, max_err, pool, q);
 }
-int launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
-                SlotPool pool, FftEntry *arena, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, unsigned *q2,
-                bool have_fwd, cudaStream_t st) {
-    // Frames that went through k_fft_fwd only run the fft2.cuh engine, which is written for any CTA size: two
-    // 256-thread CTAs per SM (same 128 registers per thread) let one frame's barriers and dependent loads
-    // overlap the other frame's arithmetic.  The fft.cuh engine of the remaining geometries needs FFT_THREADS.
-    static const int split = [] { const char *e = getenv("ATSC_FFT_SPLIT"); return e ? atoi(e) : 1; }();
-    if (!split || !have_fwd) {
-        k_fft<<<grid_for(n, pool.fft_slots / 2), FFT_THREADS, K_FFT_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool,
-                                                                                   arena, spec_xd, spec_keys, q, 0);
-        return 1;
-    }
-    k_fft<<<grid_for(n, pool.fft_slots), FFT_THREADS / 2, K_FFT_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool, arena,
-                                                                           spec_xd, spec_keys, q, 1);
+void launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
+                SlotPool pool, FftEntry *arena, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st) {
     k_fft<<<grid_for(n, pool.fft_slots / 2), FFT_THREADS, K_FFT_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool, arena,
-                                                                           spec_xd, spec_keys, q2, 2);
-    return 2;
+                                                                           spec_xd, spec_keys, q);
 }
 void launch_fft_small(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
                       FftEntry *arena, uint32_t lmax, unsigned *q, cudaStream_t st) {

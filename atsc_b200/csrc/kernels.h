@@ -50,9 +50,8 @@ void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_er
                  SlotPool pool, unsigned *q, cudaStream_t st);
 void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err, SlotPool pool,
                 unsigned *q, cudaStream_t st);
-int launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
-                SlotPool pool, FftEntry *arena, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, unsigned *q2,
-                bool have_fwd, cudaStream_t st);
+void launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
+                SlotPool pool, FftEntry *arena, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st);
 void launch_fft_small(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
                       FftEntry *arena, uint32_t lmax, unsigned *q, cudaStream_t st);
 void launch_fft_fwd(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
