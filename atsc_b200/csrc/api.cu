@@ -73,6 +73,8 @@ struct Engine {
     size_t arena_cap = 0;
     uint32_t *d_items = nullptr, *h_items = nullptr;  // frames of the wave that go through k_front
     size_t items_cap = 0;
+    float4 *d_fold = nullptr;  // k_sfold's probe folds, SF_FOLD_SLOTS per frame (sfold.cuh)
+    size_t fold_cap = 0;
     float2 *d_spec_xd = nullptr;  // per-frame half spectra of the wave (k_fft_fwd -> k_fft)
     uint32_t *d_spec_keys = nullptr;
     size_t spec_xd_cap = 0, spec_keys_cap = 0;
@@ -101,7 +103,10 @@ struct Device {
     // ATSC_FRONT=1: k_front (front.cuh) takes the big frames in one read.  Off by default: on B200 the fused
     // kernel is issue bound (profiles/r2_front_*.md) and, holding an SM's whole shared memory, cannot overlap the
     // other engines' waves, so the separate passes are still the faster pipeline (1.85 vs 2.15 ms per bench step)
-    bool front = false;
+    // ATSC_FRONT=2: k_sfold (sfold.cuh) instead: stats + the FFT probe of the big Auto frames in one read (the
+    // Polynomial candidate stays with k_poly)
+    int front = 0;
+    bool front_poly = true;  // ... including the first Polynomial step (ATSC_FRONT_POLY=0: k_poly does it)
     bool front_fold = true;  // ... including the FFT probe (ATSC_FRONT_FOLD=0: k_fft_fwd's own probe reads the samples again)
     Engine eng[MAX_ENGINES];
     uint64_t wave_samples = 0;
@@ -360,7 +365,7 @@ void engine_free(Engine &E) {
                     P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.poly_slope, P.dec_pts,
                     P.dec_mark, P.dec_idx, E.queues, E.d_ctl, E.d_frames, E.d_samples, E.d_arena, E.d_payload,
                     E.d_dec, E.d_pay_in, E.d_out, E.d_status, E.d_spec_xd, E.d_spec_keys, E.d_chunks, E.d_parts,
-                    E.d_items};
+                    E.d_items, E.d_fold};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     void *hp[] = {E.h_ctl, E.h_frames, E.h_dec, E.h_status, E.h_chunks, E.h_items};
@@ -444,8 +449,9 @@ int device_init(Device &D) {
     // waves in flight per device and samples per wave (tunable for experiments)
     D.n_engines = env_int("ATSC_ENGINES", 4, 1, MAX_ENGINES);
     D.wave_samples = (uint64_t)env_int("ATSC_WAVE_MI", 72, 1, 512) << 20;
-    D.front = env_int("ATSC_FRONT", 0, 0, 1) != 0;
+    D.front = env_int("ATSC_FRONT", 0, 0, 2);
     D.front_fold = env_int("ATSC_FRONT_FOLD", 1, 0, 1) != 0;
+    D.front_poly = env_int("ATSC_FRONT_POLY", 1, 0, 1) != 0;
     D.sms = sms;
     if ((rc = engine_init(D, D.eng[0], sms))) return rc;  // the others are set up when a call first needs them
     CK(cudaEventCreate(&D.ev_begin));
@@ -530,26 +536,41 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     uint32_t small_lmax = 2;
     // frames k_front takes: long enough, and 16-byte aligned pairs (bulk copies, double2 reads)
     const bool base_ok = D.front && ((uintptr_t)d_samples & 15u) == 0;
-    auto front_frame = [&](const FrameReq &r) {
-        // (the first Polynomial step of such a frame is 100 samples: N / max(3, N / 100), polynomial.rs:218-221)
-        return base_ok && r.len >= FRONT_MIN_SAMPLES && (r.len & 1u) == 0 && (r.off & 1ull) == 0 &&
-               r.len / std::max<uint32_t>(3, r.len / 100) == 100;
+    // frames whose FFT probe can be folded while they stream: bounded Auto, padded length 2^a * 3^7 with an even
+    // number of replicated pairs in front (fft2.cuh, fold_acc)
+    auto fold_frame = [&](const FrameReq &r) {
+        if (!(r.bounded && r.comp == C_AUTO && r.forced == 0xFF && !r.select_only && r.len >= 128)) return false;
+        const uint32_t L = padded_len(D, r.len);
+        return L % (2u * 243u) == 0 && f2_fold_ra(L / (2u * 243u)) != 0 && ((L - r.len) / 2) % 2 == 0;
     };
-    size_t n_chunks = 0, n_items = 0;
+    auto front_frame = [&](const FrameReq &r) {
+        if (!(base_ok && r.len >= FRONT_MIN_SAMPLES && (r.len & 1u) == 0 && (r.off & 1ull) == 0)) return false;
+        if (D.front == 2) return fold_frame(r);  // k_sfold
+        // (the first Polynomial step of such a frame is 100 samples: N / max(3, N / 100), polynomial.rs:218-221)
+        return r.len / std::max<uint32_t>(3, r.len / 100) == 100;
+    };
+    // k_stats chunks sit in [0, n_chunks) of the chunk table, k_sfold's slot-range items behind them; every entry
+    // has one StatsPart
+    size_t n_chunks = 0, n_items = 0, n_sf = 0, n_sf_frames = 0;
     for (uint32_t i = 0; i < n; i++) {
-        if (front_frame(reqs[i]))
-            n_items++;
-        else
+        if (!front_frame(reqs[i])) {
             n_chunks += (reqs[i].len + STATS_CHUNK - 1) / STATS_CHUNK;
+        } else if (D.front == 2) {
+            n_sf += sfold_items(padded_len(D, reqs[i].len) / (2u * 243u));
+            n_sf_frames++;
+        } else {
+            n_items++;
+        }
     }
     hcap = E.chunks_cap;
-    if ((rc = grow(D, E.st, E.d_chunks, E.chunks_cap, n_chunks))) return rc;
+    if ((rc = grow(D, E.st, E.d_chunks, E.chunks_cap, n_chunks + n_sf))) return rc;
     if ((rc = grow(D, E.st, E.h_chunks, hcap, E.chunks_cap, true))) return rc;
-    if ((rc = grow(D, E.st, E.d_parts, E.parts_cap, n_chunks))) return rc;
+    if ((rc = grow(D, E.st, E.d_parts, E.parts_cap, n_chunks + n_sf))) return rc;
+    if ((rc = grow(D, E.st, E.d_fold, E.fold_cap, n_sf_frames * (size_t)SF_FOLD_SLOTS))) return rc;
     hcap = E.items_cap;
     if ((rc = grow(D, E.st, E.d_items, E.items_cap, n_items))) return rc;
     if ((rc = grow(D, E.st, E.h_items, hcap, E.items_cap, true))) return rc;
-    uint32_t nc = 0, ni = 0;
+    uint32_t nc = 0, ni = 0, nsf = 0, nsf_frames = 0;
     for (uint32_t i = 0; i < n; i++) {
         FrameWork &f = E.h_frames[i];
         memset(&f, 0, sizeof f);
@@ -563,10 +584,16 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
         f.geom = -1;
         f.spec_off = ~0ull;
         f.chunk0 = nc;
-        if (front_frame(r)) {
+        if (D.front == 2 && front_frame(r)) {
+            f.front_mode = FM_SFOLD;
+            f.chunk0 = (uint32_t)n_chunks + nsf;
+            f.fold_slot = nsf_frames++;
+            const uint32_t slots = sfold_slots(padded_len(D, r.len) / (2u * 243u));
+            for (uint32_t s0 = 0; s0 < slots; s0 += SF_ITEM) E.h_chunks[n_chunks + nsf++] = ChunkRef{i, s0};
+        } else if (front_frame(r)) {
             f.front_mode = FM_ON;
             // the first Polynomial step is worth evaluating when the bounded Catmull-Rom loop will run
-            if (r.bounded && !r.select_only &&
+            if (D.front == 1 && D.front_poly && r.bounded && !r.select_only &&
                 (r.comp == C_POLY || (r.comp == C_AUTO && (r.forced == 0xFF || r.forced == C_POLY))))
                 f.front_mode |= FM_POLY;
             E.h_items[ni++] = i;
@@ -617,13 +644,17 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     if ((rc = grow(D, E.st, E.d_payload, E.payload_cap, (size_t)std::max<uint64_t>(samples, 1u << 20) + 64 * (size_t)n))) return rc;
     cudaStream_t st = E.st;
     CK(cudaMemcpyAsync(E.d_frames, E.h_frames, (size_t)n * sizeof(FrameWork), cudaMemcpyHostToDevice, st));
-    if (n_chunks) CK(cudaMemcpyAsync(E.d_chunks, E.h_chunks, n_chunks * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
+    if (n_chunks + n_sf) CK(cudaMemcpyAsync(E.d_chunks, E.h_chunks, (n_chunks + n_sf) * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
     if (n_items) CK(cudaMemcpyAsync(E.d_items, E.h_items, n_items * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(E.queues, 0, 64 * sizeof(unsigned), st));
     CK(cudaMemsetAsync(E.d_ctl, 0, sizeof(WaveCtl), st));
     CK(cudaEventRecord(E.ev[12], st));
     if (n_items) {
         launch_front(E.d_frames, E.d_items, (uint32_t)n_items, d_samples, max_err, D.geoms_dev, E.pool, E.queues + 9, st);
+        D.launches++;
+    }
+    if (n_sf) {
+        launch_sfold(E.d_frames, E.d_chunks + n_chunks, (uint32_t)n_sf, d_samples, D.geoms_dev, E.d_fold, E.d_parts, E.queues + 9, st);
         D.launches++;
     }
     CK(cudaEventRecord(E.ev[13], st));
@@ -633,7 +664,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
         D.launches++;
     }
     CK(cudaEventRecord(E.ev[1], st));
-    launch_plan(E.d_frames, n, d_samples, E.d_parts, st);
+    launch_plan(E.d_frames, n, d_samples, E.d_parts, D.geoms_dev, st);
     launch_poly(E.d_frames, n, d_samples, max_err, D.inv_d2, E.pool, E.queues + 1, st);
     CK(cudaEventRecord(E.ev[2], st));
     if (any_small) {
@@ -642,7 +673,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     }
     CK(cudaEventRecord(E.ev[10], st));
     if (spec) {
-        launch_fft_fwd(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_spec_xd, E.d_spec_keys, E.queues + 7, st);
+        launch_fft_fwd(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_spec_xd, E.d_spec_keys, E.d_fold, E.queues + 7, st);
         D.launches++;
     }
     CK(cudaEventRecord(E.ev[11], st));

@@ -21,6 +21,8 @@ constexpr uint8_t TIE_FFT_LOOP = 1, TIE_POLY_LOOP = 2, TIE_SELECT = 4, TIE_FFT_T
 // FrameWork.front_mode: the frame goes through k_front (stats in the streaming pass); it also evaluates
 // the first Polynomial step there; it also accumulates the FFT probe's stage-1 fold there
 constexpr uint8_t FM_ON = 1, FM_POLY = 2, FM_FOLD = 4;
+// ... or through k_sfold (sfold.cuh): its stats partials are per slot-range item and its probe fold sits in the fold arena
+constexpr uint8_t FM_SFOLD = 8;
 // FrameWork.front_res: poly_step / poly_err hold the first step's error (the loop did not end there)
 constexpr uint8_t FRES_POLY1 = 1;
 
@@ -62,7 +64,7 @@ struct FrameWork {
     uint32_t aux_size;   // Noop / Constant payload size
     uint32_t fwd_done;   // k_fft_fwd left the half spectrum + keys at spec_off
     uint32_t chunk0;     // first entry of this frame in the wave's stats chunk table
-    uint32_t pad3;
+    uint32_t fold_slot;  // FM_SFOLD: this frame's block of the wave's fold arena
     uint64_t spec_off;   // entry offset into the wave's spectrum arena (~0 = frame not eligible for fft2.cuh)
     // ---- result
     uint8_t winner, near_tie;

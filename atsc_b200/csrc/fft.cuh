@@ -64,6 +64,15 @@ struct FftGeom {
 __host__ __device__ inline uint32_t f2_fold_ra(uint32_t M1) {
     return M1 == 288u || M1 == 144u ? 16u : M1 == 72u ? 8u : M1 == 36u ? 4u : 0u;
 }
+// k_sfold (sfold.cuh): work items of SF_ITEM slots, SF_FOLD_SLOTS float4 (A, B) per frame in the wave's fold arena
+constexpr uint32_t SF_ITEM = 1458;             // a third of a full frame's 18 * 243 slots
+constexpr uint32_t SF_FOLD_SLOTS = 18u * 243u;
+// slots of a frame's fold: RB * 243 with M1 = RA * RB (0: the geometry has no probe)
+__host__ __device__ inline uint32_t sfold_slots(uint32_t M1) {
+    const uint32_t RA = f2_fold_ra(M1);
+    return RA ? (M1 / RA) * 243u : 0u;
+}
+__host__ __device__ inline uint32_t sfold_items(uint32_t M1) { return (sfold_slots(M1) + SF_ITEM - 1u) / SF_ITEM; }
 
 // per-CTA-slot global workspace
 struct FftWs {

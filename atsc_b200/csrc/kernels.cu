@@ -11,6 +11,7 @@
 #include "fft2.cuh"
 #include "fft_small.cuh"
 #include "front.cuh"
+#include "sfold.cuh"
 #include "poly.cuh"
 #include "stats.cuh"
 #include "varscan.cuh"
@@ -60,12 +61,15 @@ __global__ void __launch_bounds__(256, 8) k_stats(const FrameWork *__restrict__ 
 
 // per frame: combine the chunk partials into the stats, then decide which candidates run
 // (frame/mod.rs:71-149, compressor/mod.rs:63-107)
-__global__ void k_plan(FrameWork *fr, uint32_t n, const double *__restrict__ samples, const StatsPart *__restrict__ parts) {
+__global__ void k_plan(FrameWork *fr, uint32_t n, const double *__restrict__ samples, const StatsPart *__restrict__ parts,
+                       const FftGeom *__restrict__ geoms) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     FrameWork *fw = &fr[i];
     if (fw->front_mode & FM_ON) return;  // k_front finished this frame's stats and plan
-    finish_stats(samples + fw->off, fw->len, parts + fw->chunk0, (fw->len + STATS_CHUNK - 1) / STATS_CHUNK, fw);
+    // partials: one per 32768-sample chunk (k_stats) or per slot-range item (k_sfold)
+    const uint32_t nparts = (fw->front_mode & FM_SFOLD) ? sfold_items(geoms[fw->geom].M1) : (fw->len + STATS_CHUNK - 1) / STATS_CHUNK;
+    finish_stats(samples + fw->off, fw->len, parts + fw->chunk0, nparts, fw);
     plan_frame(fw);
 }
 
@@ -91,6 +95,21 @@ __global__ void __launch_bounds__(FR_CTA, 1) k_front(FrameWork *fr, const uint32
         if (sm->desc[fc & 1u].idx >= n_items) break;  // the producer claims the next item while a frame streams
         front_frame(fr, items, n_items, fc, samples, max_err, geoms, pool.fft_W + (size_t)blockIdx.x * MAX_FFT_LEN, q, sm, fill,
                     use, issued, nap);
+    }
+}
+
+// Stats + stage 1 of the FFT probe of the big Auto frames in one read (sfold.cuh)
+__global__ void __launch_bounds__(SF_THREADS, SF_CTAS) k_sfold(const FrameWork *__restrict__ fr, const ChunkRef *__restrict__ items,
+                                                               uint32_t n_items, const double *__restrict__ samples,
+                                                               const FftGeom *__restrict__ geoms, float4 *__restrict__ fold_arena,
+                                                               StatsPart *__restrict__ parts, unsigned *q) {
+    __shared__ StatsSmem sm;
+    __shared__ int s_item;
+    for (;;) {
+        int i = queue_next(q, &s_item);
+        if (i >= (int)n_items) break;
+        const ChunkRef ref = items[i];
+        sfold_item(&fr[ref.frame], ref.start, samples, geoms, fold_arena, parts, &sm);
     }
 }
 
@@ -413,7 +432,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fft_small(FrameWork *fr, uint32_
 __global__ void __launch_bounds__(F2_THREADS, 2) k_fft_fwd(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
                                                            double max_err, const FftGeom *__restrict__ geoms,
                                                            SlotPool pool, float2 *spec_xd, uint32_t *spec_keys,
-                                                           unsigned *q) {
+                                                           const float4 *__restrict__ fold_arena, unsigned *q) {
     extern __shared__ float2 dyn_f2[];
     __shared__ uint32_t sh[40];
     __shared__ FftGeom sg;
@@ -447,7 +466,11 @@ __global__ void __launch_bounds__(F2_THREADS, 2) k_fft_fwd(FrameWork *fr, uint32
             const uint32_t mf = (3 >= N / 100) ? 3 : N / 100;
             const uint32_t cap = min(fw->fft_list_cap, (uint32_t)FFT_KCAP);
             const uint32_t smax = sg.Bn > 65536u ? 502u : 251u;
-            uint32_t nz = block_sum_u32(f2_probe(samples + fw->off, (int)N, (int)prefix, sg, W, dyn_f2), sh);
+            uint32_t nz;
+            if (fw->front_mode & FM_SFOLD)  // k_sfold folded stage 1 while it read the frame for the stats
+                nz = block_sum_u32(f2_probe_from_fold(fold_arena + (size_t)fw->fold_slot * SF_FOLD_SLOTS, sg, W, dyn_f2), sh);
+            else
+                nz = block_sum_u32(f2_probe(samples + fw->off, (int)N, (int)prefix, sg, W, dyn_f2), sh);
             uint32_t c1 = min(min(mf, nz), cap);
             bool pruned = fft_payload_size(c1, min(c1, smax)) > bound;
             if (!pruned) {
@@ -1122,6 +1145,7 @@ int kernels_init() {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, FRONT_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
+
     e = cudaFuncSetAttribute(k_fft_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_fft_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs_smem_bytes(FS_LMAX));
@@ -1138,8 +1162,9 @@ void launch_stats(const FrameWork *fr, const ChunkRef *chunks, uint32_t n_chunks
                   unsigned *q, cudaStream_t st) {
     k_stats<<<grid_for(n_chunks, 8 * sms()), 256, 0, st>>>(fr, chunks, n_chunks, samples, parts, q);
 }
-void launch_plan(FrameWork *fr, uint32_t n, const double *samples, const StatsPart *parts, cudaStream_t st) {
-    k_plan<<<(n + 63) / 64, 64, 0, st>>>(fr, n, samples, parts);
+void launch_plan(FrameWork *fr, uint32_t n, const double *samples, const StatsPart *parts, const FftGeom *geoms,
+                 cudaStream_t st) {
+    k_plan<<<(n + 63) / 64, 64, 0, st>>>(fr, n, samples, parts, geoms);
 }
 void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_err, const double *inv_d2,
                  SlotPool pool, unsigned *q, cudaStream_t st) {
@@ -1159,9 +1184,10 @@ void launch_fft_small(FrameWork *fr, uint32_t n, const double *samples, double m
     k_fft_small<<<grid_for(n, 8 * sms()), FS_THREADS, fs_smem_bytes(lmax), st>>>(fr, n, samples, max_err, geoms, arena, lmax, q);
 }
 void launch_fft_fwd(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
-                    SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st) {
+                    SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, const float4 *fold_arena, unsigned *q,
+                    cudaStream_t st) {
     k_fft_fwd<<<grid_for(n, pool.fwd_slots), F2_THREADS, F2_SMEM_BYTES, st>>>(fr, n, samples, max_err, geoms, pool,
-                                                                             spec_xd, spec_keys, q);
+                                                                             spec_xd, spec_keys, fold_arena, q);
 }
 void launch_front(FrameWork *fr, const uint32_t *items, uint32_t n_items, const double *samples, double max_err,
                   const FftGeom *geoms, SlotPool pool, unsigned *q, cudaStream_t st) {
@@ -1169,6 +1195,10 @@ void launch_front(FrameWork *fr, const uint32_t *items, uint32_t n_items, const 
     static const uint32_t nap = getenv("ATSC_FRONT_NAP") ? (uint32_t)atoi(getenv("ATSC_FRONT_NAP")) : 64u;
     k_front<<<grid_for(n_items, sms()), FR_CTA, FRONT_SMEM_BYTES, st>>>(fr, items, n_items, samples, max_err, geoms, pool, q,
                                                                         nap);
+}
+void launch_sfold(const FrameWork *fr, const ChunkRef *items, uint32_t n_items, const double *samples, const FftGeom *geoms,
+                  float4 *fold_arena, StatsPart *parts, unsigned *q, cudaStream_t st) {
+    k_sfold<<<grid_for(n_items, SF_CTAS * sms()), SF_THREADS, 0, st>>>(fr, items, n_items, samples, geoms, fold_arena, parts, q);
 }
 void launch_noop_size(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st) {
     k_noop_size<<<grid_for(n, 2 * sms()), BLOCK, 0, st>>>(fr, n, samples, q);

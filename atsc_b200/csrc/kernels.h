@@ -45,7 +45,8 @@ struct DecFrame {
 // compress pipeline; q = device array of >= 8 zeroed uint32 work-queue counters
 void launch_stats(const FrameWork *fr, const ChunkRef *chunks, uint32_t n_chunks, const double *samples, StatsPart *parts,
                   unsigned *q, cudaStream_t st);
-void launch_plan(FrameWork *fr, uint32_t n, const double *samples, const StatsPart *parts, cudaStream_t st);
+void launch_plan(FrameWork *fr, uint32_t n, const double *samples, const StatsPart *parts, const FftGeom *geoms,
+                 cudaStream_t st);
 void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_err, const double *inv_d2,
                  SlotPool pool, unsigned *q, cudaStream_t st);
 void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err, SlotPool pool,
@@ -55,8 +56,12 @@ void launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err
 void launch_fft_small(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
                       FftEntry *arena, uint32_t lmax, unsigned *q, cudaStream_t st);
 void launch_fft_fwd(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,
-                    SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, unsigned *q, cudaStream_t st);
+                    SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, const float4 *fold_arena, unsigned *q,
+                    cudaStream_t st);
 // fused front end (front.cuh) of the frames items[0 .. n_items): frames with FM_ON set by the host
+// stats + probe fold (sfold.cuh) of the frames with FM_SFOLD: items = (frame, first slot) pairs
+void launch_sfold(const FrameWork *fr, const ChunkRef *items, uint32_t n_items, const double *samples, const FftGeom *geoms,
+                  float4 *fold_arena, StatsPart *parts, unsigned *q, cudaStream_t st);
 void launch_front(FrameWork *fr, const uint32_t *items, uint32_t n_items, const double *samples, double max_err,
                   const FftGeom *geoms, SlotPool pool, unsigned *q, cudaStream_t st);
 constexpr uint32_t FRONT_MIN_SAMPLES = 16384;  // == FRONT_MIN_LEN (front.cuh)

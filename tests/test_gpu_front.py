@@ -34,6 +34,25 @@ def ctxs():
     off.close()
 
 
+@pytest.fixture(scope="module")
+def sfold_ctxs():
+    """k_sfold (ATSC_FRONT=2: stats + FFT probe in one read, sfold.cuh) against the separate passes."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import atsc_b200
+    made = []
+    for v in ("2", "0"):
+        os.environ["ATSC_FRONT"] = v
+        try:
+            made.append(atsc_b200.Context())
+        finally:
+            os.environ.pop("ATSC_FRONT")
+    yield made
+    for c in made:
+        c.close()
+
+
 def front_frames():
     """Frames of >= 16384 samples that exercise every branch of the streaming pass."""
     rng = np.random.default_rng(77)
@@ -140,3 +159,40 @@ def test_front_stats_bytes(ctxs):
         got = run_batch(on, arrays, comp, bounded=False)
         for (name, a), (o, b) in zip(cs, got):
             assert b == O.compress(comp, a), f"{O.NAMES[comp]} {name}"
+
+
+@pytest.mark.parametrize("err,speed", [(0.05, 0), (0.01, 0), (0.0, 0), (0.05, 6), (0.3, 0)])
+def test_sfold_matches_separate_passes(sfold_ctxs, err, speed):
+    on, off = sfold_ctxs
+    cs = front_frames()
+    arrays = [a for _, a in cs]
+    names = [n for n, _ in cs]
+    r_on = run_batch(on, arrays, O.AUTO, max_error=err, speed=speed)
+    r_off = run_batch(off, arrays, O.AUTO, max_error=err, speed=speed)
+    same_records(r_on, r_off, names, f"sfold Auto e={err} c={speed}")
+    if speed == 0:
+        assert on.kernel_ms(reset=True)["front"] > 0.0, "k_sfold did not run"
+
+
+def test_sfold_against_oracle(sfold_ctxs):
+    on, _ = sfold_ctxs
+    cs = [c for c in front_frames() if not c[0].startswith(("nan",))]
+    got = run_batch(on, [a for _, a in cs], O.AUTO, max_error=0.05)
+    bad = []
+    for (name, a), (o, b) in zip(cs, got):
+        wc, wb, _, _ = O.compress_best(a, np.float32(0.05), 0)
+        if (o.compressor != wc or (wc != O.FFT and b != wb)) and not o.near_tie:
+            bad.append(name)
+    assert not bad, bad
+
+
+def test_sfold_mixed_batch_and_other_compressors(sfold_ctxs):
+    """Frames k_sfold does not take (other compressors, odd lengths) share a wave with frames it does."""
+    on, off = sfold_ctxs
+    cs = front_frames()[:14]
+    arrays = [a for _, a in cs] + [gen.make("util", 5000, 1), gen.make("periodic", 131071, 2)]
+    names = [n for n, _ in cs] + ["util5000", "periodic131071"]
+    for comp in (O.AUTO, O.RLE, O.POLYNOMIAL, O.FFT):
+        r_on = run_batch(on, arrays, comp, max_error=0.05)
+        r_off = run_batch(off, arrays, comp, max_error=0.05)
+        same_records(r_on, r_off, names, f"sfold {O.NAMES[comp]}")
