@@ -75,6 +75,7 @@ struct Engine {
     size_t items_cap = 0;
     float4 *d_fold = nullptr;  // k_sfold's probe folds, SF_FOLD_SLOTS per frame (sfold.cuh)
     size_t fold_cap = 0;
+    std::vector<uint8_t> fronted;  // issue_wave scratch
     float2 *d_spec_xd = nullptr;  // per-frame half spectra of the wave (k_fft_fwd -> k_fft)
     uint32_t *d_spec_keys = nullptr;
     size_t spec_xd_cap = 0, spec_keys_cap = 0;
@@ -100,12 +101,14 @@ struct Device {
     int id = 0;
     cudaStream_t st = nullptr;  // setup stream (tables)
     int n_engines = 0, sms = 0;
-    // ATSC_FRONT=1: k_front (front.cuh) takes the big frames in one read.  Off by default: on B200 the fused
-    // kernel is issue bound (profiles/r2_front_*.md) and, holding an SM's whole shared memory, cannot overlap the
-    // other engines' waves, so the separate passes are still the faster pipeline (1.85 vs 2.15 ms per bench step)
-    // ATSC_FRONT=2: k_sfold (sfold.cuh) instead: stats + the FFT probe of the big Auto frames in one read (the
-    // Polynomial candidate stays with k_poly)
-    int front = 0;
+    // Front end of the big frames (ATSC_FRONT):
+    //   2 (default): k_sfold (sfold.cuh) reads the big Auto frames once for the stats AND stage 1 of the FFT
+    //      probe; the Polynomial candidate stays with k_poly.  +1.8 % on the bench fleet over the separate passes.
+    //   1: k_front (front.cuh) also evaluates the first Polynomial step in that single read.  On B200 the fused
+    //      kernel is issue bound and, holding an SM's whole shared memory, cannot overlap the other engines' waves:
+    //      8.16 vs 6.36 ms per bench step, so it is opt-in.
+    //   0: separate passes (k_stats, k_poly, k_fft_fwd's own probe).
+    int front = 2;
     bool front_poly = true;  // ... including the first Polynomial step (ATSC_FRONT_POLY=0: k_poly does it)
     bool front_fold = true;  // ... including the FFT probe (ATSC_FRONT_FOLD=0: k_fft_fwd's own probe reads the samples again)
     Engine eng[MAX_ENGINES];
@@ -449,7 +452,7 @@ int device_init(Device &D) {
     // waves in flight per device and samples per wave (tunable for experiments)
     D.n_engines = env_int("ATSC_ENGINES", 4, 1, MAX_ENGINES);
     D.wave_samples = (uint64_t)env_int("ATSC_WAVE_MI", 72, 1, 512) << 20;
-    D.front = env_int("ATSC_FRONT", 0, 0, 2);
+    D.front = env_int("ATSC_FRONT", 2, 0, 2);
     D.front_fold = env_int("ATSC_FRONT_FOLD", 1, 0, 1) != 0;
     D.front_poly = env_int("ATSC_FRONT_POLY", 1, 0, 1) != 0;
     D.sms = sms;
@@ -552,10 +555,15 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     // k_stats chunks sit in [0, n_chunks) of the chunk table, k_sfold's slot-range items behind them; every entry
     // has one StatsPart
     size_t n_chunks = 0, n_items = 0, n_sf = 0, n_sf_frames = 0;
+    std::vector<uint8_t> &fronted = E.fronted;  // per frame: does a front-end kernel take it
+    fronted.assign(n, 0);
     for (uint32_t i = 0; i < n; i++) {
-        if (!front_frame(reqs[i])) {
+        if (!D.front || !front_frame(reqs[i])) {
             n_chunks += (reqs[i].len + STATS_CHUNK - 1) / STATS_CHUNK;
-        } else if (D.front == 2) {
+            continue;
+        }
+        fronted[i] = 1;
+        if (D.front == 2) {
             n_sf += sfold_items(padded_len(D, reqs[i].len) / (2u * 243u));
             n_sf_frames++;
         } else {
@@ -584,13 +592,13 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
         f.geom = -1;
         f.spec_off = ~0ull;
         f.chunk0 = nc;
-        if (D.front == 2 && front_frame(r)) {
+        if (D.front == 2 && fronted[i]) {
             f.front_mode = FM_SFOLD;
             f.chunk0 = (uint32_t)n_chunks + nsf;
             f.fold_slot = nsf_frames++;
             const uint32_t slots = sfold_slots(padded_len(D, r.len) / (2u * 243u));
             for (uint32_t s0 = 0; s0 < slots; s0 += SF_ITEM) E.h_chunks[n_chunks + nsf++] = ChunkRef{i, s0};
-        } else if (front_frame(r)) {
+        } else if (fronted[i]) {
             f.front_mode = FM_ON;
             // the first Polynomial step is worth evaluating when the bounded Catmull-Rom loop will run
             if (D.front == 1 && D.front_poly && r.bounded && !r.select_only &&
