@@ -76,6 +76,9 @@ struct Engine {
     float4 *d_fold = nullptr;  // k_sfold's probe folds, SF_FOLD_SLOTS per frame (sfold.cuh)
     size_t fold_cap = 0;
     std::vector<uint8_t> fronted;  // issue_wave scratch
+    ChunkRef *d_pitems = nullptr, *h_pitems = nullptr;  // k_poly1 work items (frame, part)
+    double *d_ppart = nullptr;                          // their partial MAPE sums
+    size_t pitems_cap = 0, ppart_cap = 0;
     float2 *d_spec_xd = nullptr;  // per-frame half spectra of the wave (k_fft_fwd -> k_fft)
     uint32_t *d_spec_keys = nullptr;
     size_t spec_xd_cap = 0, spec_keys_cap = 0;
@@ -109,6 +112,7 @@ struct Device {
     //      8.16 vs 6.36 ms per bench step, so it is opt-in.
     //   0: separate passes (k_stats, k_poly, k_fft_fwd's own probe).
     int front = 2;
+    bool poly_items = true;  // ATSC_POLY_ITEMS=0: k_poly evaluates the first step of the big frames itself
     bool front_poly = true;  // ... including the first Polynomial step (ATSC_FRONT_POLY=0: k_poly does it)
     bool front_fold = true;  // ... including the FFT probe (ATSC_FRONT_FOLD=0: k_fft_fwd's own probe reads the samples again)
     Engine eng[MAX_ENGINES];
@@ -368,10 +372,10 @@ void engine_free(Engine &E) {
                     P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.poly_slope, P.dec_pts,
                     P.dec_mark, P.dec_idx, E.queues, E.d_ctl, E.d_frames, E.d_samples, E.d_arena, E.d_payload,
                     E.d_dec, E.d_pay_in, E.d_out, E.d_status, E.d_spec_xd, E.d_spec_keys, E.d_chunks, E.d_parts,
-                    E.d_items, E.d_fold};
+                    E.d_items, E.d_fold, E.d_pitems, E.d_ppart};
     for (void *p : ptrs)
         if (p) cudaFree(p);
-    void *hp[] = {E.h_ctl, E.h_frames, E.h_dec, E.h_status, E.h_chunks, E.h_items};
+    void *hp[] = {E.h_ctl, E.h_frames, E.h_dec, E.h_status, E.h_chunks, E.h_items, E.h_pitems};
     for (void *p : hp)
         if (p) cudaFreeHost(p);
     for (auto &ev : E.ev)
@@ -455,6 +459,7 @@ int device_init(Device &D) {
     D.front = env_int("ATSC_FRONT", 2, 0, 2);
     D.front_fold = env_int("ATSC_FRONT_FOLD", 1, 0, 1) != 0;
     D.front_poly = env_int("ATSC_FRONT_POLY", 1, 0, 1) != 0;
+    D.poly_items = env_int("ATSC_POLY_ITEMS", 1, 0, 1) != 0;
     D.sms = sms;
     if ((rc = engine_init(D, D.eng[0], sms))) return rc;  // the others are set up when a call first needs them
     CK(cudaEventCreate(&D.ev_begin));
@@ -570,6 +575,19 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
             n_items++;
         }
     }
+    // frames whose first Polynomial step k_poly1 evaluates in balanced work items (poly.cuh)
+    auto poly1_frame = [&](const FrameReq &r) {
+        return D.poly_items && r.len >= POLY_ITEM_MIN_LEN && r.bounded && !r.select_only &&
+               (r.comp == C_POLY || (r.comp == C_AUTO && (r.forced == 0xFF || r.forced == C_POLY)));
+    };
+    size_t n_pitems = 0;
+    if (D.front != 1)
+        for (uint32_t i = 0; i < n; i++)
+            if (poly1_frame(reqs[i])) n_pitems += poly_item_count(reqs[i].len);
+    hcap = E.pitems_cap;
+    if ((rc = grow(D, E.st, E.d_pitems, E.pitems_cap, n_pitems))) return rc;
+    if ((rc = grow(D, E.st, E.h_pitems, hcap, E.pitems_cap, true))) return rc;
+    if ((rc = grow(D, E.st, E.d_ppart, E.ppart_cap, n_pitems))) return rc;
     hcap = E.chunks_cap;
     if ((rc = grow(D, E.st, E.d_chunks, E.chunks_cap, n_chunks + n_sf))) return rc;
     if ((rc = grow(D, E.st, E.h_chunks, hcap, E.chunks_cap, true))) return rc;
@@ -578,7 +596,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     hcap = E.items_cap;
     if ((rc = grow(D, E.st, E.d_items, E.items_cap, n_items))) return rc;
     if ((rc = grow(D, E.st, E.h_items, hcap, E.items_cap, true))) return rc;
-    uint32_t nc = 0, ni = 0, nsf = 0, nsf_frames = 0;
+    uint32_t nc = 0, ni = 0, nsf = 0, nsf_frames = 0, npi = 0;
     for (uint32_t i = 0; i < n; i++) {
         FrameWork &f = E.h_frames[i];
         memset(&f, 0, sizeof f);
@@ -607,6 +625,11 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
             E.h_items[ni++] = i;
         } else {
             for (uint32_t c0 = 0; c0 < r.len; c0 += STATS_CHUNK) E.h_chunks[nc++] = ChunkRef{i, c0};
+        }
+        if (n_pitems && poly1_frame(r)) {
+            f.poly_part0 = npi;
+            f.poly_parts = poly_item_count(r.len);
+            for (uint32_t q = 0; q < f.poly_parts; q++) E.h_pitems[npi++] = ChunkRef{i, q};
         }
         samples += r.len;
         uint8_t eff = (r.comp == C_AUTO && r.forced != 0xFF) ? r.forced : r.comp;
@@ -654,6 +677,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     CK(cudaMemcpyAsync(E.d_frames, E.h_frames, (size_t)n * sizeof(FrameWork), cudaMemcpyHostToDevice, st));
     if (n_chunks + n_sf) CK(cudaMemcpyAsync(E.d_chunks, E.h_chunks, (n_chunks + n_sf) * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
     if (n_items) CK(cudaMemcpyAsync(E.d_items, E.h_items, n_items * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (n_pitems) CK(cudaMemcpyAsync(E.d_pitems, E.h_pitems, n_pitems * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(E.queues, 0, 64 * sizeof(unsigned), st));
     CK(cudaMemsetAsync(E.d_ctl, 0, sizeof(WaveCtl), st));
     CK(cudaEventRecord(E.ev[12], st));
@@ -673,7 +697,11 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     }
     CK(cudaEventRecord(E.ev[1], st));
     launch_plan(E.d_frames, n, d_samples, E.d_parts, D.geoms_dev, st);
-    launch_poly(E.d_frames, n, d_samples, max_err, D.inv_d2, E.pool, E.queues + 1, st);
+    if (n_pitems) {
+        launch_poly1(E.d_frames, E.d_pitems, (uint32_t)n_pitems, d_samples, E.d_ppart, E.queues + 11, st);
+        D.launches++;
+    }
+    launch_poly(E.d_frames, n, d_samples, max_err, D.inv_d2, E.pool, E.d_ppart, E.queues + 1, st);
     CK(cudaEventRecord(E.ev[2], st));
     if (any_small) {
         launch_fft_small(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.d_arena, small_lmax, E.queues + 8, st);

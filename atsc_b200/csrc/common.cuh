@@ -26,6 +26,11 @@ constexpr uint8_t FM_SFOLD = 8;
 // FrameWork.front_res: poly_step / poly_err hold the first step's error (the loop did not end there)
 constexpr uint8_t FRES_POLY1 = 1;
 
+// k_poly1 (poly.cuh: poly_first_step_item): work items of the first Polynomial step of the big frames
+constexpr uint32_t POLY_ITEM = 32768;          // samples per item
+constexpr uint32_t POLY_ITEM_MIN_LEN = 65536;  // frames this long go through k_poly1 (step 100, >= 2 items)
+__host__ __device__ inline uint32_t poly_item_count(uint32_t N) { return (N + POLY_ITEM - 1) / POLY_ITEM; }
+
 // One record per frame, lives in device memory for the duration of a wave.
 struct FrameWork {
     // ---- input
@@ -65,6 +70,7 @@ struct FrameWork {
     uint32_t fwd_done;   // k_fft_fwd left the half spectrum + keys at spec_off
     uint32_t chunk0;     // first entry of this frame in the wave's stats chunk table
     uint32_t fold_slot;  // FM_SFOLD: this frame's block of the wave's fold arena
+    uint32_t poly_part0, poly_parts;  // k_poly1: first entry / number of this frame's first-step partial sums (0: none)
     uint64_t spec_off;   // entry offset into the wave's spectrum arena (~0 = frame not eligible for fft2.cuh)
     // ---- result
     uint8_t winner, near_tie;

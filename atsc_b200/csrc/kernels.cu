@@ -116,9 +116,30 @@ __global__ void __launch_bounds__(SF_THREADS, SF_CTAS) k_sfold(const FrameWork *
 // =========================================================================================
 // polynomial / idw
 // =========================================================================================
+// first candidate step of the big Catmull-Rom frames, in balanced work items (poly.cuh: poly_first_step_item)
+__global__ void __launch_bounds__(512, 2) k_poly1(const FrameWork *__restrict__ fr, const ChunkRef *__restrict__ items,
+                                                 uint32_t n_items, const double *__restrict__ samples,
+                                                 double *__restrict__ parts, unsigned *q) {
+    __shared__ double shd[64];
+    __shared__ double tang[POLY_ITEM_KEYS];
+    __shared__ int s_item;
+    for (;;) {
+        int i = queue_next(q, &s_item);
+        if (i >= (int)n_items) break;
+        const ChunkRef ref = items[i];
+        const FrameWork *fw = &fr[ref.frame];
+        // the frames poly_frame would evaluate this step for (bounded Catmull-Rom, not "same max and min")
+        if (!fw->need_poly || fw->poly_type || fw->poly_valid || !fw->bounded || fw->vmax == fw->vmin) continue;
+        const double *d = samples + fw->off;
+        double *out = parts + fw->poly_part0 + ref.start;
+        if (poly_tame(fw->vmin, fw->vmax)) poly_first_step_item<true>(d, fw->len, fw->vmin, fw->vmax, ref.start, out, tang, shd);
+        else poly_first_step_item<false>(d, fw->len, fw->vmin, fw->vmax, ref.start, out, tang, shd);
+    }
+}
+
 __global__ void __launch_bounds__(512, 2) k_poly(FrameWork *fr, uint32_t n, const double *__restrict__ samples,
                                                 double max_err, const double *__restrict__ inv_d2, SlotPool pool,
-                                                unsigned *q) {
+                                                const double *__restrict__ first_parts, unsigned *q) {
     __shared__ double shd[64];
     __shared__ int s_item;
     PolyWs ws;
@@ -128,7 +149,7 @@ __global__ void __launch_bounds__(512, 2) k_poly(FrameWork *fr, uint32_t n, cons
         if (i >= (int)n) break;
         FrameWork *fw = &fr[i];
         if (!fw->need_poly || fw->poly_valid) continue;  // poly_valid: k_front settled it at the first step
-        poly_frame(samples + fw->off, fw, max_err, inv_d2, shd, ws);
+        poly_frame(samples + fw->off, fw, max_err, inv_d2, shd, ws, first_parts);
     }
 }
 
@@ -1167,8 +1188,12 @@ void launch_plan(FrameWork *fr, uint32_t n, const double *samples, const StatsPa
     k_plan<<<(n + 63) / 64, 64, 0, st>>>(fr, n, samples, parts, geoms);
 }
 void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_err, const double *inv_d2,
-                 SlotPool pool, unsigned *q, cudaStream_t st) {
-    k_poly<<<grid_for(n, pool.poly_slots), 512, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, q);
+                 SlotPool pool, const double *first_parts, unsigned *q, cudaStream_t st) {
+    k_poly<<<grid_for(n, pool.poly_slots), 512, 0, st>>>(fr, n, samples, max_err, inv_d2, pool, first_parts, q);
+}
+void launch_poly1(const FrameWork *fr, const ChunkRef *items, uint32_t n_items, const double *samples, double *parts,
+                  unsigned *q, cudaStream_t st) {
+    k_poly1<<<grid_for(n_items, 2 * sms()), 512, 0, st>>>(fr, items, n_items, samples, parts, q);
 }
 void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err, SlotPool pool, unsigned *q,
                 cudaStream_t st) {

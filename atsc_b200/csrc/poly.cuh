@@ -168,6 +168,73 @@ __device__ inline double poly_mape_ends(const double *__restrict__ d, const Poly
     return acc;
 }
 
+// This thread's share of a Catmull-Rom step's MAPE sum over the segments of the NS-blocks [b_lo, b_hi)
+// (block b = segments 1 + NS*b .. NS*b + NS), plus -- `tail` -- the fewer-than-NS segments left over
+// behind the last whole block.  tang[j - tbase] is the tangent of key j (global or shared memory).
+// Thread t owns one offset j inside the segments (its Hermite basis values stay in registers) and
+// walks over segments, so the inner loop has no table lookups, no index division and no branches.
+constexpr int POLY_NS = 4;
+template <bool TAME>
+__device__ inline double poly_cr_range(const double *__restrict__ d, const PolyKeys &k, double vmin, double vmax,
+                                       const double *__restrict__ tang, uint32_t tbase, uint32_t b_lo, uint32_t b_hi, bool tail) {
+    const uint32_t step = k.step, K = k.K, T = blockDim.x, t = threadIdx.x;
+    const double stepd = (double)step;
+    double acc = 0.0;
+    tang -= tbase;
+    // Catmull-Rom segments 1 .. K-3 (polynomial.rs:349: key i is CatmullRom iff 0 < i < K-2)
+    const uint32_t G = T / step, g = t / step, j = t - g * step;  // G groups of `step` threads
+    if (g < G && K >= 4) {
+        const double tt = __ddiv_rn((double)j, stepd);
+        const double two_t = __dmul_rn(tt, 2.0), three_t = __dmul_rn(tt, 3.0);
+        const double t2 = __dmul_rn(tt, tt), t3 = __dmul_rn(t2, tt);
+        const double two_t3 = __dmul_rn(t2, two_t), two_t2 = __dmul_rn(tt, two_t), three_t2 = __dmul_rn(tt, three_t);
+        const double h00 = __dadd_rn(__dsub_rn(two_t3, three_t2), 1.0), h10 = __dadd_rn(__dsub_rn(t3, two_t2), tt);
+        const double h01 = __dsub_rn(three_t2, two_t3), h11 = __dsub_rn(t3, t2);
+        const uint32_t i_hi = K - 3;  // inclusive; keys i and i+1 are regular for every i <= K-3
+        auto term = [&](double v, double o) -> double {
+            return TAME ? mape_term_tame(round_and_limit5_tame(v, vmin, vmax), o)
+                        : mape_term(round_and_limit5_fast(v, vmin, vmax), o);
+        };
+        auto hermite = [&](double av, double ta, double bv, double tb) -> double {
+            return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(av, h00), __dmul_rn(ta, h10)), __dmul_rn(bv, h01)),
+                             __dmul_rn(tb, h11));
+        };
+        auto seg_err = [&](uint32_t i) -> double {
+            const uint32_t xa = i * step;
+            return term(hermite(d[xa], tang[i], d[xa + step], tang[i + 1]), d[xa + j]);
+        };
+        // NS adjacent segments per trip through running pointers: the NS - 1 inner keys and tangents are
+        // loaded once for the two segments they belong to, and 3 * NS + 2 loads are in flight per thread.
+        // The loop waits on memory, not on issue slots: with the same arithmetic, two segments per trip
+        // took 1.00 ms per bench step, two with one-trip-ahead register prefetch 0.89, four 0.78 (B200).
+        constexpr int NS = POLY_NS;
+        const uint32_t nblk = i_hi / NS;  // segments 1 .. i_hi in blocks of NS
+        const double *p = d + (size_t)(1 + NS * (b_lo + g)) * step, *tg = tang + 1 + NS * (b_lo + g);
+        const double *po = p + j;  // this thread's samples
+        const size_t stride = (size_t)NS * G * step;
+        for (uint32_t q = b_lo + g; q < b_hi; q += G) {
+            double kv[NS + 1], tv[NS + 1], o[NS], e[NS];
+#pragma unroll
+            for (int u = 0; u <= NS; u++) {
+                kv[u] = p[(uint32_t)u * step];
+                tv[u] = tg[u];
+            }
+#pragma unroll
+            for (int u = 0; u < NS; u++) o[u] = po[(uint32_t)u * step];
+#pragma unroll
+            for (int u = 0; u < NS; u++) e[u] = term(hermite(kv[u], tv[u], kv[u + 1], tv[u + 1]), o[u]);
+#pragma unroll
+            for (int u = 0; u < NS; u++) acc += e[u];
+            p += stride;
+            po += stride;
+            tg += NS * G;
+        }
+        if (tail)
+            for (uint32_t i = nblk * NS + 1 + g; i <= i_hi; i += G) acc += seg_err(i);  // fewer than NS left over
+    }
+    return acc;
+}
+
 // MAPE (utils/error.rs:104-116) of one candidate step against the frame; block-wide.
 // Catmull-Rom path: identical value arithmetic to poly_eval_at (same operations, same order).
 // Thread t owns one offset j inside the segments (its Hermite basis values stay in registers) and
@@ -199,59 +266,44 @@ __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys 
         tang[j] = __dmul_rn(__ddiv_rn(__dsub_rn(d[pb], d[pa]), __dsub_rn((double)pb, (double)pa)), stepd);
     }
     __syncthreads();
-    // ---- Catmull-Rom segments 1 .. K-3 (polynomial.rs:349: key i is CatmullRom iff 0 < i < K-2)
-    const uint32_t G = T / step, g = t / step, j = t - g * step;  // G groups of `step` threads
-    if (g < G && K >= 4) {
-        const double tt = __ddiv_rn((double)j, stepd);
-        const double two_t = __dmul_rn(tt, 2.0), three_t = __dmul_rn(tt, 3.0);
-        const double t2 = __dmul_rn(tt, tt), t3 = __dmul_rn(t2, tt);
-        const double two_t3 = __dmul_rn(t2, two_t), two_t2 = __dmul_rn(tt, two_t), three_t2 = __dmul_rn(tt, three_t);
-        const double h00 = __dadd_rn(__dsub_rn(two_t3, three_t2), 1.0), h10 = __dadd_rn(__dsub_rn(t3, two_t2), tt);
-        const double h01 = __dsub_rn(three_t2, two_t3), h11 = __dsub_rn(t3, t2);
-        const uint32_t i_hi = K - 3;  // inclusive; keys i and i+1 are regular for every i <= K-3
-        auto term = [&](double v, double o) -> double {
-            return TAME ? mape_term_tame(round_and_limit5_tame(v, vmin, vmax), o)
-                        : mape_term(round_and_limit5_fast(v, vmin, vmax), o);
-        };
-        auto hermite = [&](double av, double ta, double bv, double tb) -> double {
-            return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(av, h00), __dmul_rn(ta, h10)), __dmul_rn(bv, h01)),
-                             __dmul_rn(tb, h11));
-        };
-        auto seg_err = [&](uint32_t i) -> double {
-            const uint32_t xa = i * step;
-            return term(hermite(d[xa], tang[i], d[xa + step], tang[i + 1]), d[xa + j]);
-        };
-        // NS adjacent segments per trip through running pointers: the NS - 1 inner keys and tangents are
-        // loaded once for the two segments they belong to, and 3 * NS + 2 loads are in flight per thread.
-        // The loop waits on memory, not on issue slots: with the same arithmetic, two segments per trip
-        // took 1.00 ms per bench step, two with one-trip-ahead register prefetch 0.89, four 0.78 (B200).
-        constexpr int NS = 4;
-        const uint32_t nblk = i_hi / NS;  // segments 1 .. i_hi in blocks of NS
-        const double *p = d + (size_t)(1 + NS * g) * step, *tg = tang + 1 + NS * g;
-        const double *po = p + j;  // this thread's samples
-        const size_t stride = (size_t)NS * G * step;
-        for (uint32_t q = g; q < nblk; q += G) {
-            double kv[NS + 1], tv[NS + 1], o[NS], e[NS];
-#pragma unroll
-            for (int u = 0; u <= NS; u++) {
-                kv[u] = p[(uint32_t)u * step];
-                tv[u] = tg[u];
-            }
-#pragma unroll
-            for (int u = 0; u < NS; u++) o[u] = po[(uint32_t)u * step];
-#pragma unroll
-            for (int u = 0; u < NS; u++) e[u] = term(hermite(kv[u], tv[u], kv[u + 1], tv[u + 1]), o[u]);
-#pragma unroll
-            for (int u = 0; u < NS; u++) acc += e[u];
-            p += stride;
-            po += stride;
-            tg += NS * G;
-        }
-        for (uint32_t i = nblk * NS + 1 + g; i <= i_hi; i += G) acc += seg_err(i);  // fewer than NS left over
-    }
+    if (K >= 4) acc += poly_cr_range<TAME>(d, k, vmin, vmax, tang, 0u, 0u, (K - 3) / POLY_NS, true);
     acc += poly_mape_ends(d, k, vmin, vmax);
     double s = block_sum(acc, scratch);
     return __ddiv_rn(s, (double)N);
+}
+
+// k_poly1: the FIRST candidate step of a big bounded Catmull-Rom frame, cut into POLY_ITEM-sample work items so
+// that the pass balances over the SMs (a wave of the bench fleet holds ~340 full frames for 296 CTA slots: whole
+// frames leave a quarter of the SM time idle).  Item q of Q = poly_item_count(N) takes the NS-blocks
+// [nblk * q / Q, nblk * (q + 1) / Q) of the step poly_frame tries first, the last item also the left-over segments
+// and the Linear ends; its tangents live in shared memory.  The MAPE is a sum: the items' partial sums are added
+// in item order by poly_frame, which goes on from there exactly as if it had evaluated the step itself.
+constexpr uint32_t POLY_ITEM_KEYS = 352;       // tangents of one item (<= 82 blocks of 4 segments + the tail)
+__host__ __device__ inline uint32_t poly_first_step(uint32_t N) {
+    const uint32_t baseline = (3 >= N / 100) ? 3 : N / 100;  // polynomial.rs:218-221
+    const uint32_t step = N / baseline;
+    return step < 1 ? 1 : step;
+}
+template <bool TAME>
+__device__ inline void poly_first_step_item(const double *__restrict__ d, uint32_t N, double vmin, double vmax, uint32_t q,
+                                            double *part_out, double *tang_sm, double *scratch) {
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    const PolyKeys k = poly_keys(N, poly_first_step(N));
+    const uint32_t K = k.K, Q = poly_item_count(N), nblk = (K - 3) / POLY_NS;
+    const uint32_t b_lo = (uint32_t)((uint64_t)nblk * q / Q), b_hi = (uint32_t)((uint64_t)nblk * (q + 1) / Q);
+    const bool tail = q + 1 == Q;
+    const uint32_t j_lo = 1 + POLY_NS * b_lo, j_hi = tail ? K - 2 : POLY_NS * b_hi + 1;  // keys whose tangent is used
+    const double stepd = (double)k.step;
+    for (uint32_t j = j_lo + t; j <= j_hi; j += T) {
+        const uint32_t pa = poly_pos(k, j - 1), pb = poly_pos(k, j + 1);
+        tang_sm[j - j_lo] = __dmul_rn(__ddiv_rn(__dsub_rn(d[pb], d[pa]), __dsub_rn((double)pb, (double)pa)), stepd);
+    }
+    __syncthreads();
+    double acc = poly_cr_range<TAME>(d, k, vmin, vmax, tang_sm, j_lo, b_lo, b_hi, tail);
+    if (tail) acc += poly_mape_ends(d, k, vmin, vmax);
+    const double s = block_sum(acc, scratch);
+    if (t == 0) *part_out = s;
+    __syncthreads();
 }
 
 // Polynomial::polynomial_to_data (polynomial.rs:342-373) + round_and_limit_f64 for a whole frame:
@@ -381,7 +433,8 @@ __device__ inline bool poly_loop_near_tie(double cur, double target) {
 // Runs the reference's refinement loop for one frame. All threads of the CTA call.
 // Writes poly_* fields of fw (thread 0).  `sh` = shared scratch (>= 40 doubles).
 __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, double max_err,
-                                  const double *__restrict__ inv_d2, double *sh, PolyWs ws) {
+                                  const double *__restrict__ inv_d2, double *sh, PolyWs ws,
+                                  const double *__restrict__ first_parts) {
     const uint32_t N = fw->len;
     const double vmin = fw->vmin, vmax = fw->vmax;
     const int ptype = fw->poly_type;
@@ -416,6 +469,11 @@ __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, d
                     cur = 0.0;  // value unused: the `len == data_len` exit below overrides it
                 } else if (it == 1 && (fw->front_res & FRES_POLY1) && step == fw->poly_step) {
                     cur = fw->poly_err;  // k_front evaluated this step while it streamed the frame
+                } else if (it == 1 && fw->poly_parts && ptype == 0) {
+                    // k_poly1 evaluated this step in poly_parts work items: add their sums in item order
+                    double sum = 0.0;
+                    for (uint32_t q = 0; q < fw->poly_parts; q++) sum += first_parts[fw->poly_part0 + q];
+                    cur = __ddiv_rn(sum, (double)N);
                 } else {
                     cur = tame ? poly_mape<true>(d, k, ptype, vmin, vmax, inv_d2, ws, sh)
                                : poly_mape<false>(d, k, ptype, vmin, vmax, inv_d2, ws, sh);

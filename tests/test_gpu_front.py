@@ -196,3 +196,42 @@ def test_sfold_mixed_batch_and_other_compressors(sfold_ctxs):
         r_on = run_batch(on, arrays, comp, max_error=0.05)
         r_off = run_batch(off, arrays, comp, max_error=0.05)
         same_records(r_on, r_off, names, f"sfold {O.NAMES[comp]}")
+
+
+@pytest.fixture(scope="module")
+def poly_item_ctxs():
+    """k_poly1 (first Polynomial step of frames >= 65536 samples in balanced work items, poly.cuh) on / off."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import atsc_b200
+    made = []
+    for v in ("1", "0"):
+        os.environ["ATSC_POLY_ITEMS"] = v
+        os.environ["ATSC_FRONT"] = "0"
+        try:
+            made.append(atsc_b200.Context())
+        finally:
+            os.environ.pop("ATSC_POLY_ITEMS")
+            os.environ.pop("ATSC_FRONT")
+    yield made
+    for c in made:
+        c.close()
+
+
+@pytest.mark.parametrize("comp,err", [(O.AUTO, 0.05), (O.AUTO, 0.002), (O.POLYNOMIAL, 0.05), (O.POLYNOMIAL, 0.001),
+                                      (O.POLYNOMIAL, 0.0), (O.IDW, 0.05)])
+def test_poly_items_match_whole_frames(poly_item_ctxs, comp, err):
+    on, off = poly_item_ctxs
+    cs = [c for c in front_frames() if len(c[1]) >= 65536 or c[0] in ("util20000", "gauge16386")]
+    if comp == O.IDW:
+        cs = cs[:2]
+    arrays = [a for _, a in cs]
+    names = [n for n, _ in cs]
+    r_on = run_batch(on, arrays, comp, max_error=err)
+    r_off = run_batch(off, arrays, comp, max_error=err)
+    same_records(r_on, r_off, names, f"poly items {O.NAMES[comp]} e={err}")
+    if comp == O.POLYNOMIAL:
+        for (name, a), (o, b) in zip(cs, r_on):
+            if not o.near_tie and not name.startswith("nan"):
+                assert b == O.compress_bounded(comp, a, np.float32(err))[0], name
