@@ -21,8 +21,8 @@
 namespace atsc {
 
 constexpr int SF_THREADS = 256;
-constexpr int SF_CTAS = 5;            // per SM
-constexpr int SF_U = 2;               // 16-byte loads in flight per thread
+constexpr int SF_CTAS = 4;            // per SM
+constexpr int SF_U = 4;               // 16-byte loads in flight per thread
 
 // One element of a slot's chain: the sample pair p (or a gibbs replica), stats + run ends + fold term.
 //   HEAD / TAIL: the element may be a replica of the first / last sample (only chunk 0 / chunk RA-1 hold any)

@@ -583,7 +583,12 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     dom = max(("stats", "poly", "rle", "fft_fwd", "fft_small", "fft", "select", "emit", "front"), key=lambda k: kms[k])  # host_issue is not a kernel
     dom_ms = kms[dom] / args.steps
-    dom_samples = n_samples if dom in ("stats", "select", "front") else fft_samples
+    front_mode = os.environ.get("ATSC_FRONT", "2")  # api.cu: 2 = k_sfold (default), 1 = k_front, 0 = separate passes
+    kname = {"front": "k_sfold" if front_mode == "2" else "k_front", "poly": "k_poly"}
+    big_samples = int(lens[lens >= 16384].astype(np.int64).sum())  # the frames the front-end kernel takes
+    fftwin_samples = int(lens[comps == atsc_b200.FFT].astype(np.int64).sum())  # frames k_fft_fwd transforms in full
+    dom_samples = {"stats": n_samples - (big_samples if front_mode != "0" else 0), "select": n_samples, "front": big_samples,
+                   "fft_fwd": fft_samples if front_mode == "0" else fftwin_samples}.get(dom, fft_samples)
     achieved = dom_samples * 8 / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     # the same kernels timed without other waves sharing the GPU (one engine): explains how much of
     # the in-pipeline duration above is contention
@@ -612,18 +617,26 @@ def main():
     traffic, traffic_detail = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic_detail = tj.get("k_" + dom)
+        traffic_detail = tj.get(kname.get(dom, "k_" + dom))
         if traffic_detail:
             traffic = traffic_detail["bytes_per_launch"]
     except Exception:
         pass
-    alg1 = {"stats": 288 * SERIES_LEN * 8, "poly": 192 * SERIES_LEN * 8, "fft_fwd": 192 * SERIES_LEN * 8}
+    # algorithmic bytes of a 288-series call: every sample once for the stats pass (k_stats + the front-end kernel),
+    # the non-constant frames for k_poly (+ k_poly1), the frames transformed in full for k_fft_fwd
+    per_series = 288.0 / S
+    alg1 = {"stats": 288 * SERIES_LEN * 8, "poly": 192 * SERIES_LEN * 8,
+            "fft_fwd": (fft_samples if front_mode == "0" else fftwin_samples) * per_series * 8}
     one_engine = None
     if iso and "error" not in iso:
-        one_engine = {"k_" + k: {"ms_per_288_series": round(iso[k], 4), "achieved": alg1[k] / (iso[k] * 1e-3) / 1e9,
-                                 "frac": alg1[k] / (iso[k] * 1e-3) / 1e9 / peak}
-                      for k in alg1 if iso.get(k)}
-    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        iso1 = dict(iso)
+        iso1["stats"] = iso.get("stats", 0.0) + iso.get("front", 0.0)
+        names1 = {"stats": "k_stats" if front_mode == "0" else "k_stats+" + kname["front"], "poly": "k_poly+k_poly1",
+                  "fft_fwd": "k_fft_fwd"}
+        one_engine = {names1[k]: {"ms_per_288_series": round(iso1[k], 4), "achieved": alg1[k] / (iso1[k] * 1e-3) / 1e9,
+                                  "frac": alg1[k] / (iso1[k] * 1e-3) / 1e9 / peak}
+                      for k in alg1 if iso1.get(k)}
+    roofline = {"bound": "hbm", "kernel": kname.get(dom, "k_" + dom), "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_detail": traffic_detail, "one_engine": one_engine,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_step": dom_samples * 8,
@@ -633,9 +646,10 @@ def main():
                 "note": "achieved / frac / kernel_ms_per_step: CUDA events on each engine's stream inside the timed region "
                         "(waves of several engines overlap, so these durations include contention and add up to more "
                         "than the step); one_engine: the same kernels on a 288-series call with a single engine, i.e. each "
-                        "launch alone on the GPU, which is the figure to hold against the kernel's own roofline; k_poly and "
-                        "k_fft_fwd wait on loads (ncu long-scoreboard stalls), k_stats runs near the HBM line (DESIGN.md "
-                        "section 4); the HBM line is the task's stated denominator"}
+                        "launch alone on the GPU, which is the figure to hold against the kernel's own roofline (k_sfold / k_front "
+                        "are reported under 'front'; 'poly' covers k_plan + k_poly1 + k_poly); k_poly and k_fft_fwd wait on "
+                        "loads (ncu long-scoreboard stalls), the stats pass runs nearer the HBM line (DESIGN.md section 4); "
+                        "the HBM line is the task's stated denominator"}
 
     # ---- decompression of the fleet just produced (device-resident output)
     frames_in = []
