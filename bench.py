@@ -568,7 +568,7 @@ def main():
     step_host()
     dt_e2e, _ = timed(step_host, e2e_steps, "compress_e2e")
     e2e_v = world * n_samples * e2e_steps / dt_e2e / 1e6
-    d2h = int(len(payload)) + len(lens) * 168
+    d2h = int(len(payload)) + len(lens) * 176  # payload + one FrameWork record per frame (csrc/common.cuh)
 
     # ---- roofline of the dominant kernel
     comps = np.array([out[i].compressor for i in range(len(lens))])
@@ -584,7 +584,8 @@ def main():
     dom = max(("stats", "poly", "rle", "fft_fwd", "fft_small", "fft", "select", "emit", "front"), key=lambda k: kms[k])  # host_issue is not a kernel
     dom_ms = kms[dom] / args.steps
     front_mode = os.environ.get("ATSC_FRONT", "2")  # api.cu: 2 = k_sfold (default), 1 = k_front, 0 = separate passes
-    kname = {"front": "k_sfold" if front_mode == "2" else "k_front", "poly": "k_poly"}
+    kname = {"front": "k_sfold" if front_mode == "2" else "k_front",
+             "poly": "k_poly1+k_poly" if os.environ.get("ATSC_POLY_ITEMS", "1") != "0" else "k_poly"}
     big_samples = int(lens[lens >= 16384].astype(np.int64).sum())  # the frames the front-end kernel takes
     fftwin_samples = int(lens[comps == atsc_b200.FFT].astype(np.int64).sum())  # frames k_fft_fwd transforms in full
     dom_samples = {"stats": n_samples - (big_samples if front_mode != "0" else 0), "select": n_samples, "front": big_samples,
@@ -617,9 +618,14 @@ def main():
     traffic, traffic_detail = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic_detail = tj.get(kname.get(dom, "k_" + dom))
-        if traffic_detail:
-            traffic = traffic_detail["bytes_per_launch"]
+        if dom == "poly" and "k_poly1" in tj and os.environ.get("ATSC_POLY_ITEMS", "1") != "0":
+            # the 'poly' slot times k_plan + k_poly1 + k_poly: one wave's launches of both kernels
+            traffic_detail = {"k_poly1": tj["k_poly1"], "k_poly": {k: v for k, v in tj["k_poly"].items() if k != "whole_frames"}}
+            traffic = tj["k_poly1"]["bytes_per_launch"] + tj["k_poly"]["bytes_per_launch"]
+        else:
+            traffic_detail = tj.get(kname.get(dom, "k_" + dom))
+            if traffic_detail:
+                traffic = traffic_detail["bytes_per_launch"]
     except Exception:
         pass
     # algorithmic bytes of a 288-series call: every sample once for the stats pass (k_stats + the front-end kernel),

@@ -69,6 +69,22 @@ def test_library_holds_sm100a_code_for_every_kernel():
         pytest.skip("cuobjdump not available")
     r = subprocess.run([cuobjdump, "-elf", atsc_b200.lib_path()], capture_output=True, text=True, timeout=300)
     assert "sm_100a" in r.stdout or "sm_100" in r.stdout
-    for k in ("k_stats", "k_plan", "k_poly", "k_fft_small", "k_fft_fwd", "k_fft", "k_rle", "k_noop_size", "k_select",
-              "k_scan", "k_emit", "k_decode"):
+    for k in ("k_stats", "k_sfold", "k_front", "k_plan", "k_poly1", "k_poly", "k_fft_small", "k_fft_fwd", "k_fft", "k_rle",
+              "k_noop_size", "k_select", "k_scan", "k_emit", "k_decode"):
         assert f"atsc{len(k)}{k}" in r.stdout, k      # Itanium-mangled atsc::k_*
+
+
+def test_bulk_async_staging_in_the_shipped_sass():
+    """k_front stages frames with cp.async.bulk + mbarrier transactions: the sm_100a cubin must hold the
+    bulk-copy and transaction-barrier instructions (profiles/r2_k_front_sass.md)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    r = subprocess.run([cuobjdump, "-sass", "-fun", "k_front", atsc_b200.lib_path()], capture_output=True, text=True, timeout=600)
+    text = r.stdout
+    if "UBLKCP" not in text:  # older cuobjdump: -fun wants the mangled name; fall back to the whole library
+        text = subprocess.run([cuobjdump, "-sass", atsc_b200.lib_path()], capture_output=True, text=True, timeout=900).stdout
+    assert "UBLKCP" in text, "no bulk asynchronous copy in the SASS"
+    assert "SYNCS" in text, "no mbarrier transaction instruction in the SASS"
