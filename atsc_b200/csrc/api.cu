@@ -112,6 +112,7 @@ struct Device {
     //      8.16 vs 6.36 ms per bench step, so it is opt-in.
     //   0: separate passes (k_stats, k_poly, k_fft_fwd's own probe).
     int front = 2;
+    bool probe_kernel = true;  // ATSC_PROBE_KERNEL=0: k_fft_fwd runs the probe tails of k_sfold's frames itself
     bool poly_items = true;  // ATSC_POLY_ITEMS=0: k_poly evaluates the first step of the big frames itself
     bool front_poly = true;  // ... including the first Polynomial step (ATSC_FRONT_POLY=0: k_poly does it)
     bool front_fold = true;  // ... including the FFT probe (ATSC_FRONT_FOLD=0: k_fft_fwd's own probe reads the samples again)
@@ -460,6 +461,7 @@ int device_init(Device &D) {
     D.front_fold = env_int("ATSC_FRONT_FOLD", 1, 0, 1) != 0;
     D.front_poly = env_int("ATSC_FRONT_POLY", 1, 0, 1) != 0;
     D.poly_items = env_int("ATSC_POLY_ITEMS", 1, 0, 1) != 0;
+    D.probe_kernel = env_int("ATSC_PROBE_KERNEL", 1, 0, 1) != 0;
     D.sms = sms;
     if ((rc = engine_init(D, D.eng[0], sms))) return rc;  // the others are set up when a call first needs them
     CK(cudaEventCreate(&D.ev_begin));
@@ -600,6 +602,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     if ((rc = grow(D, E.st, E.d_parts, E.parts_cap, n_chunks + n_sf))) return rc;
     if ((rc = grow(D, E.st, E.d_fold, E.fold_cap, n_sf_frames * (size_t)SF_FOLD_SLOTS))) return rc;
     hcap = E.items_cap;
+    if (D.front == 2) n_items = n_sf_frames;  // k_probe's list: the frames k_sfold folds
     if ((rc = grow(D, E.st, E.d_items, E.items_cap, n_items))) return rc;
     if ((rc = grow(D, E.st, E.h_items, hcap, E.items_cap, true))) return rc;
     uint32_t nc = 0, ni = 0, nsf = 0, nsf_frames = 0, npi = 0;
@@ -620,6 +623,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
             f.front_mode = FM_SFOLD;
             f.chunk0 = (uint32_t)n_chunks + nsf;
             f.fold_slot = nsf_frames++;
+            E.h_items[ni++] = i;
             const uint32_t slots = sfold_slots(padded_len(D, r.len) / (2u * 243u));
             for (uint32_t s0 = 0; s0 < slots; s0 += SF_ITEM) E.h_chunks[n_chunks + nsf++] = ChunkRef{i, s0};
         } else if (fronted[i]) {
@@ -687,7 +691,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     CK(cudaMemsetAsync(E.queues, 0, 64 * sizeof(unsigned), st));
     CK(cudaMemsetAsync(E.d_ctl, 0, sizeof(WaveCtl), st));
     CK(cudaEventRecord(E.ev[12], st));
-    if (n_items) {
+    if (n_items && D.front == 1) {
         launch_front(E.d_frames, E.d_items, (uint32_t)n_items, d_samples, max_err, D.geoms_dev, E.pool, E.queues + 9, st);
         D.launches++;
     }
@@ -714,6 +718,10 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
         D.launches++;
     }
     CK(cudaEventRecord(E.ev[10], st));
+    if (spec && n_sf && D.probe_kernel) {
+        launch_probe(E.d_frames, E.d_items, (uint32_t)n_items, max_err, D.geoms_dev, E.d_fold, E.queues + 12, st);
+        D.launches++;
+    }
     if (spec) {
         launch_fft_fwd(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.pool, E.d_spec_xd, E.d_spec_keys, E.d_fold, E.queues + 7, st);
         D.launches++;

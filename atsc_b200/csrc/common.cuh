@@ -25,6 +25,8 @@ constexpr uint8_t FM_ON = 1, FM_POLY = 2, FM_FOLD = 4;
 constexpr uint8_t FM_SFOLD = 8;
 // FrameWork.front_res: poly_step / poly_err hold the first step's error (the loop did not end there)
 constexpr uint8_t FRES_POLY1 = 1;
+// ... k_probe found enough nonzero bins and the FFT candidate is NOT pruned: k_fft_fwd goes straight to the transform
+constexpr uint8_t FRES_SURVIVOR = 4;
 
 // k_poly1 (poly.cuh: poly_first_step_item): work items of the first Polynomial step of the big frames
 constexpr uint32_t POLY_ITEM = 32768;          // samples per item

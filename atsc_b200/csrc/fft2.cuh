@@ -661,4 +661,90 @@ __device__ inline uint32_t f2_probe_from_fold(const float4 *__restrict__ fold, c
     return f2_probe_pass2((int)g.M1, RA, g.tw2, g.twL1, g.twL2, W, sm);
 }
 
+// ---------------------------------------------------------------------------------------
+// SMALL PROBE from a fold (k_probe): the pruning rule only needs "at least c nonzero bins" with
+// c <= max_freq (fft.rs:249-252), so `np` row pairs (k1 = 1 + RA*pl and its partner M1 - k1, pl < np:
+// 2 * np * 243 bins) are enough whenever they are all nonzero -- the usual case.  Same expressions as
+// f2_fold_stage2 / f2_probe_pass2 on those rows (bit-identical bins); everything after the fold stays in
+// shared memory (smW, smY: 2 * np * 243 float2 each).  Returns this thread's count of nonzero bins.
+// ---------------------------------------------------------------------------------------
+constexpr int F2_PROBE_NP = 4;  // pairs at most: 8 rows
+template <int RA, int RB>
+__device__ inline uint32_t f2_probe_small_t(const float4 *__restrict__ fold, const FftGeom &g, int np, float2 *smW,
+                                            float2 *smY) {
+    constexpr int M1 = RA * RB;
+    const int tid = threadIdx.x, nth = blockDim.x, rows = 2 * np;
+    // pass-1 stage 2 of the two families; only the rows of the first np pairs are kept
+    for (int item = tid; item < 2 * F2_M2; item += nth) {
+        const int fam = item & 1, c = item >> 1;  // fam 0: q = 1, fam 1: q = RA-1
+        const int q = fam ? RA - 1 : 1;
+        float2 b[RB];
+#pragma unroll
+        for (int t = 0; t < RB; t++) {
+            float2 s1, sR;
+            fold_out(__ldcg(fold + t * F2_M2 + c), s1, sR);
+            b[t] = cmul(fam ? sR : s1, __ldg(g.tw1 + t * q));
+        }
+        DftS<RB, 1, false>::run(b);
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            const int pl = fam ? RB - 1 - u : u;  // the pair this row belongs to
+            if (pl < np) {
+                const int k1 = q + RA * u, lr = fam ? np + pl : pl;
+                smW[c * rows + lr] = cmul(b[u], __ldg(g.T4 + c * M1 + k1));
+            }
+        }
+    }
+    __syncthreads();
+    // pass 2, stage 1: item (p < 9, compact row lr)
+    for (int item = tid; item < 9 * rows; item += nth) {
+        const int p = item / rows, lr = item - p * rows;
+        float2 a[27];
+#pragma unroll
+        for (int t = 0; t < 27; t++) a[t] = smW[(p + 9 * t) * rows + lr];
+        DftS<27, 1, false>::run(a);
+        float2 *y = smY + lr * F2_M2 + 27 * p;
+        y[0] = a[0];
+#pragma unroll
+        for (int q = 1; q < 27; q++) y[q] = cmul(a[q], __ldg(g.tw2 + p * q));
+    }
+    __syncthreads();
+    // pass 2, stage 2: item (pair pl < np, q < 27): rows k1 (element q) and M1-k1 (element 26-q) together
+    uint32_t nz = 0;
+    for (int item = tid; item < np * 27; item += nth) {
+        const int q = item % 27, pl = item / 27;
+        float2 A[9], B[9];
+        const float2 *ya = smY + pl * F2_M2 + q, *yb = smY + (pl + np) * F2_M2 + (26 - q);
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            A[t] = ya[27 * t];
+            B[t] = yb[27 * t];
+        }
+        DftS<9, 1, false>::run(A);
+        DftS<9, 1, false>::run(B);
+        const int k1 = 1 + RA * pl;
+        const float2 w1 = __ldg(g.twL1 + k1);
+#pragma unroll
+        for (int u = 0; u < 9; u++) {
+            const int k2 = q + 27 * u;
+            const float2 w = cmul(w1, __ldg(g.twL2 + k2));
+            const float2 Xk = f2_post(A[u], B[8 - u], w);
+            const float2 Xm = f2_post(B[8 - u], A[u], make_float2(-w.x, w.y));
+            nz += (Xk.x != 0.f || Xk.y != 0.f) ? 1u : 0u;
+            nz += (Xm.x != 0.f || Xm.y != 0.f) ? 1u : 0u;
+        }
+    }
+    __syncthreads();
+    return nz;
+}
+__device__ inline uint32_t f2_probe_small(const float4 *__restrict__ fold, const FftGeom &g, int np, float2 *smW, float2 *smY) {
+    switch (g.M1) {
+        case 288: return f2_probe_small_t<16, 18>(fold, g, np, smW, smY);
+        case 144: return f2_probe_small_t<16, 9>(fold, g, np, smW, smY);
+        case 72: return f2_probe_small_t<8, 9>(fold, g, np, smW, smY);
+        case 36: return f2_probe_small_t<4, 9>(fold, g, np, smW, smY);
+        default: return 0u;
+    }
+}
+
 }  // namespace atsc

@@ -447,6 +447,60 @@ __global__ void __launch_bounds__(FS_THREADS) k_fft_small(FrameWork *fr, uint32_
     }
 }
 
+// What a later candidate allows the FFT payload of an Auto frame to be: FFT wins only with
+// size <= every passing candidate after it, and wins ties (frame/mod.rs:77,94-147).  ~0: no bound.
+__device__ inline uint32_t fft_prune_bound(const FrameWork *fw, double max_err) {
+    uint32_t bound = 0xFFFFFFFFu;
+    if (fw->bounded && fw->comp == C_AUTO && fw->forced == 0xFF) {
+        if (fw->poly_valid == 1 && fw->poly_err <= max_err) bound = min(bound, fw->poly_size);
+        if (fw->need_rle) bound = min(bound, fw->rle_valid == 1 ? fw->rle_size : rle_upper_bound(fw));  // RLE's error is 0: it always passes
+    }
+    return bound;
+}
+
+// Probe tails of the frames k_sfold folded (sfold.cuh): small CTAs, everything after the fold in shared
+// memory, only as many row pairs as the first schedule point can use (fft2.cuh: f2_probe_small).  A frame
+// whose probed bins are all nonzero is settled here -- pruned (fft_valid = 2), or marked FRES_SURVIVOR so
+// that k_fft_fwd transforms it without probing; the rare sparse spectrum is left to k_fft_fwd's full-row probe.
+__global__ void __launch_bounds__(128, 5) k_probe(FrameWork *fr, const uint32_t *__restrict__ items, uint32_t n_items, double max_err,
+                                                 const FftGeom *__restrict__ geoms, const float4 *__restrict__ fold_arena,
+                                                 unsigned *q) {
+    __shared__ float2 smW[2 * F2_PROBE_NP * F2_M2], smY[2 * F2_PROBE_NP * F2_M2];
+    __shared__ uint32_t sh[40];
+    __shared__ FftGeom sg;
+    __shared__ int s_item;
+    const uint32_t t = threadIdx.x;
+    for (;;) {
+        int i = queue_next(q, &s_item);
+        if (i >= (int)n_items) break;
+        FrameWork *fw = &fr[items[i]];
+        if (!(fw->front_mode & FM_SFOLD) || !fw->need_fft || fw->f32_const || fw->geom < 0 || fw->spec_off == ~0ull) continue;
+        const uint32_t bound = fft_prune_bound(fw, max_err);
+        if (bound == 0xFFFFFFFFu) continue;
+        if (t == 0) sg = geoms[fw->geom];
+        __syncthreads();
+        const uint32_t N = fw->len, mf = (3 >= N / 100) ? 3 : N / 100;
+        const uint32_t want = min(mf, min(fw->fft_list_cap, (uint32_t)FFT_KCAP));  // entries of the first schedule point
+        const uint32_t RB = sg.M1 / f2_fold_ra(sg.M1);
+        const int np = (int)min(min((want + 485u) / 486u + 1u, (uint32_t)F2_PROBE_NP), RB);
+        const uint32_t nz = block_sum_u32(f2_probe_small(fold_arena + (size_t)fw->fold_slot * SF_FOLD_SLOTS, sg, np, smW, smY), sh);
+        if (nz < want) continue;  // zero bins among the probed ones: not decided here
+        const uint32_t smax = sg.Bn > 65536u ? 502u : 251u;
+        if (t == 0) {
+            if (fft_payload_size(want, min(want, smax)) > bound) {
+                fw->fft_count = want;
+                fw->fft_err = max_err + 1.0;
+                fw->fft_size = 0;
+                fw->fft_iters = 1;
+                fw->fft_tie = 0;
+                fw->fft_valid = 2;  // proven unable to win
+            } else {
+                fw->front_res |= FRES_SURVIVOR;
+            }
+        }
+    }
+}
+
 // forward transform (fft2.cuh) of every eligible frame, ahead of k_fft.  Auto frames whose first
 // schedule point is already larger than a passing Polynomial / RLE payload end here (fft_valid = 2)
 // without ever storing a spectrum; everything else leaves Xd / keys in the wave's spectrum arena.
@@ -474,12 +528,11 @@ __global__ void __launch_bounds__(F2_THREADS, 2) k_fft_fwd(FrameWork *fr, uint32
         float2 *Xd = spec_xd + fw->spec_off;
         uint32_t *keys = spec_keys + fw->spec_off;
         // a later candidate can only lose to FFT on size; FFT wins ties (frame/mod.rs:77,104,141)
-        uint32_t bound = 0xFFFFFFFFu;
-        if (bounded && fw->comp == C_AUTO && fw->forced == 0xFF) {
-            if (fw->poly_valid == 1 && fw->poly_err <= max_err) bound = min(bound, fw->poly_size);
-            if (fw->need_rle) bound = min(bound, fw->rle_valid == 1 ? fw->rle_size : rle_upper_bound(fw));  // RLE's error is 0: it always passes
-        }
-        if (bound != 0xFFFFFFFFu) {
+        const uint32_t bound = fft_prune_bound(fw, max_err);
+        if (bound != 0xFFFFFFFFu && (fw->front_res & FRES_SURVIVOR)) {
+            // k_probe: enough nonzero bins for the first schedule point, and that point fits the bound
+            f2_forward_pass1(samples + fw->off, (int)N, (int)prefix, sg, W, dyn_f2);
+        } else if (bound != 0xFFFFFFFFu) {
             // The first schedule point keeps c1 = min(max_freq, #nonzero bins) entries (fft.rs:249-252),
             // at most `smax` of them with a one-byte position, and the payload only grows from there.
             // A probe of 1/8 of the spectrum (bit-identical to the full transform on those bins) usually
@@ -1224,6 +1277,10 @@ void launch_front(FrameWork *fr, const uint32_t *items, uint32_t n_items, const 
 void launch_sfold(const FrameWork *fr, const ChunkRef *items, uint32_t n_items, const double *samples, const FftGeom *geoms,
                   float4 *fold_arena, StatsPart *parts, unsigned *q, cudaStream_t st) {
     k_sfold<<<grid_for(n_items, SF_CTAS * sms()), SF_THREADS, 0, st>>>(fr, items, n_items, samples, geoms, fold_arena, parts, q);
+}
+void launch_probe(FrameWork *fr, const uint32_t *items, uint32_t n_items, double max_err, const FftGeom *geoms,
+                  const float4 *fold_arena, unsigned *q, cudaStream_t st) {
+    k_probe<<<grid_for(n_items, 5 * sms()), 128, 0, st>>>(fr, items, n_items, max_err, geoms, fold_arena, q);
 }
 void launch_noop_size(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st) {
     k_noop_size<<<grid_for(n, 2 * sms()), BLOCK, 0, st>>>(fr, n, samples, q);

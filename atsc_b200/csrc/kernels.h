@@ -62,6 +62,9 @@ void launch_fft_fwd(FrameWork *fr, uint32_t n, const double *samples, double max
                     SlotPool pool, float2 *spec_xd, uint32_t *spec_keys, const float4 *fold_arena, unsigned *q,
                     cudaStream_t st);
 // fused front end (front.cuh) of the frames items[0 .. n_items): frames with FM_ON set by the host
+// probe tails (fft2.cuh: f2_probe_small) of the frames items[0 .. n_items) that k_sfold folded
+void launch_probe(FrameWork *fr, const uint32_t *items, uint32_t n_items, double max_err, const FftGeom *geoms,
+                  const float4 *fold_arena, unsigned *q, cudaStream_t st);
 // stats + probe fold (sfold.cuh) of the frames with FM_SFOLD: items = (frame, first slot) pairs
 void launch_sfold(const FrameWork *fr, const ChunkRef *items, uint32_t n_items, const double *samples, const FftGeom *geoms,
                   float4 *fold_arena, StatsPart *parts, unsigned *q, cudaStream_t st);

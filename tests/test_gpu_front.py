@@ -235,3 +235,33 @@ def test_poly_items_match_whole_frames(poly_item_ctxs, comp, err):
         for (name, a), (o, b) in zip(cs, r_on):
             if not o.near_tie and not name.startswith("nan"):
                 assert b == O.compress_bounded(comp, a, np.float32(err))[0], name
+
+
+def test_probe_kernel_matches_in_kernel_probe():
+    """k_probe (small probe tails, decided frames skip k_fft_fwd's probe) against ATSC_PROBE_KERNEL=0."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import atsc_b200
+    made = []
+    for v in ("1", "0"):
+        os.environ["ATSC_PROBE_KERNEL"] = v
+        try:
+            made.append(atsc_b200.Context())
+        finally:
+            os.environ.pop("ATSC_PROBE_KERNEL")
+    try:
+        cs = front_frames()
+        # sparse spectra: an exact DC step and a two-level square wave leave most probed bins at zero
+        a = np.zeros(131072); a[:65536] = 5.0; a += 10.0
+        cs.append(("dc_step", a))
+        cs.append(("lin_ramp_int", np.arange(65536, dtype=np.float64) + 1.0))
+        arrays = [x for _, x in cs]
+        names = [n for n, _ in cs]
+        for err in (0.05, 0.0005):
+            r1 = run_batch(made[0], arrays, O.AUTO, max_error=err)
+            r0 = run_batch(made[1], arrays, O.AUTO, max_error=err)
+            same_records(r1, r0, names, f"probe kernel e={err}")
+    finally:
+        for c in made:
+            c.close()
