@@ -462,7 +462,7 @@ __device__ inline uint32_t fft_prune_bound(const FrameWork *fw, double max_err) 
 // memory, only as many row pairs as the first schedule point can use (fft2.cuh: f2_probe_small).  A frame
 // whose probed bins are all nonzero is settled here -- pruned (fft_valid = 2), or marked FRES_SURVIVOR so
 // that k_fft_fwd transforms it without probing; the rare sparse spectrum is left to k_fft_fwd's full-row probe.
-__global__ void __launch_bounds__(128, 5) k_probe(FrameWork *fr, const uint32_t *__restrict__ items, uint32_t n_items, double max_err,
+__global__ void __launch_bounds__(192, 3) k_probe(FrameWork *fr, const uint32_t *__restrict__ items, uint32_t n_items, double max_err,
                                                  const FftGeom *__restrict__ geoms, const float4 *__restrict__ fold_arena,
                                                  unsigned *q) {
     __shared__ float2 smW[2 * F2_PROBE_NP * F2_M2], smY[2 * F2_PROBE_NP * F2_M2];
@@ -1280,7 +1280,7 @@ void launch_sfold(const FrameWork *fr, const ChunkRef *items, uint32_t n_items, 
 }
 void launch_probe(FrameWork *fr, const uint32_t *items, uint32_t n_items, double max_err, const FftGeom *geoms,
                   const float4 *fold_arena, unsigned *q, cudaStream_t st) {
-    k_probe<<<grid_for(n_items, 5 * sms()), 128, 0, st>>>(fr, items, n_items, max_err, geoms, fold_arena, q);
+    k_probe<<<grid_for(n_items, 3 * sms()), 192, 0, st>>>(fr, items, n_items, max_err, geoms, fold_arena, q);
 }
 void launch_noop_size(FrameWork *fr, uint32_t n, const double *samples, unsigned *q, cudaStream_t st) {
     k_noop_size<<<grid_for(n, 2 * sms()), BLOCK, 0, st>>>(fr, n, samples, q);
