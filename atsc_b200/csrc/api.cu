@@ -71,7 +71,7 @@ struct Engine {
     size_t samples_cap = 0;
     FftEntry *d_arena = nullptr;
     size_t arena_cap = 0;
-    uint32_t *d_items = nullptr, *h_items = nullptr;  // frames of the wave that go through k_front
+    uint32_t *d_items = nullptr, *h_items = nullptr;  // frames of the wave that go through k_front, or (k_sfold) k_probe's list
     size_t items_cap = 0;
     float4 *d_fold = nullptr;  // k_sfold's probe folds, SF_FOLD_SLOTS per frame (sfold.cuh)
     size_t fold_cap = 0;
@@ -94,7 +94,7 @@ struct Engine {
     uint32_t *d_status = nullptr, *h_status = nullptr;
     size_t status_cap = 0;
     // CUDA events around every kernel of the wave (kernel_ms)
-    cudaEvent_t ev[14] = {};  // 0-7 compress pipeline, 8-9 decode, 10-11 between the FFT kernels, 12-13 k_front
+    cudaEvent_t ev[14] = {};  // 0-7 compress pipeline, 8-9 decode, 10-11 between the FFT kernels, 12-13 front end (k_sfold / k_front)
     WaveJob job;
     bool dec_active = false;  // a decode wave is pending on this engine
     uint32_t dec_pos = 0, dec_n = 0;
@@ -544,7 +544,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     uint64_t arena = 0, spec = 0, samples = 0;
     bool any_noop = false, any_small = false, any_large = false;
     uint32_t small_lmax = 2;
-    // frames k_front takes: long enough, and 16-byte aligned pairs (bulk copies, double2 reads)
+    // frames a front-end kernel takes: long enough, and 16-byte aligned pairs (bulk copies, double2 reads)
     const bool base_ok = D.front && ((uintptr_t)d_samples & 15u) == 0;
     // frames whose FFT probe can be folded while they stream: bounded Auto, padded length 2^a * 3^7 with an even
     // number of replicated pairs in front (fft2.cuh, fold_acc)

@@ -1,5 +1,6 @@
-"""k_front (fused stats + first Polynomial step + FFT probe fold, one read of the frame) against the
-separate passes (ATSC_FRONT=0) and against the CPU oracle: same frame records, same payload bytes.
+"""The front ends of the big frames against each other and against the CPU oracle: k_front (ATSC_FRONT=1: stats +
+first Polynomial step + FFT probe fold in one read), k_sfold (ATSC_FRONT=2, the default: stats + probe fold, with
+k_probe), the separate passes (ATSC_FRONT=0), and k_poly1's work items: same frame records, same payload bytes.
 Reference behaviour under test: frame/mod.rs:71-149, polynomial.rs:209-277, optimizer/utils.rs:39-89."""
 import os
 
