@@ -77,8 +77,10 @@ struct Engine {
     size_t fold_cap = 0;
     std::vector<uint8_t> fronted;  // issue_wave scratch
     ChunkRef *d_pitems = nullptr, *h_pitems = nullptr;  // k_poly1 work items (frame, part)
-    double *d_ppart = nullptr;                          // their partial MAPE sums
-    size_t pitems_cap = 0, ppart_cap = 0;
+    double *d_ppart = nullptr;                          // their partial MAPE sums (P1_PARTS per item with k_poly1s)
+    P1Item *d_p1list = nullptr;                         // k_poly1_prep's compacted descriptors for k_poly1s
+    double2 *d_p1kt = nullptr;                          // ... and (key, tangent) pairs, POLY_ITEM_KEYS per item
+    size_t pitems_cap = 0, ppart_cap = 0, p1list_cap = 0, p1kt_cap = 0;
     float2 *d_spec_xd = nullptr;  // per-frame half spectra of the wave (k_fft_fwd -> k_fft)
     uint32_t *d_spec_keys = nullptr;
     size_t spec_xd_cap = 0, spec_keys_cap = 0;
@@ -114,6 +116,7 @@ struct Device {
     int front = 2;
     bool probe_kernel = true;  // ATSC_PROBE_KERNEL=0: k_fft_fwd runs the probe tails of k_sfold's frames itself
     bool poly_items = true;  // ATSC_POLY_ITEMS=0: k_poly evaluates the first step of the big frames itself
+    bool poly1_static = true;  // ATSC_POLY1_STATIC=0: the queue-driven k_poly1 instead of k_poly1_prep + k_poly1s (A/B runs)
     bool front_poly = true;  // ... including the first Polynomial step (ATSC_FRONT_POLY=0: k_poly does it)
     bool front_fold = true;  // ... including the FFT probe (ATSC_FRONT_FOLD=0: k_fft_fwd's own probe reads the samples again)
     Engine eng[MAX_ENGINES];
@@ -373,7 +376,7 @@ void engine_free(Engine &E) {
                     P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.poly_slope, P.dec_pts,
                     P.dec_mark, P.dec_idx, E.queues, E.d_ctl, E.d_frames, E.d_samples, E.d_arena, E.d_payload,
                     E.d_dec, E.d_pay_in, E.d_out, E.d_status, E.d_spec_xd, E.d_spec_keys, E.d_chunks, E.d_parts,
-                    E.d_items, E.d_fold, E.d_pitems, E.d_ppart};
+                    E.d_items, E.d_fold, E.d_pitems, E.d_ppart, E.d_p1list, E.d_p1kt};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     void *hp[] = {E.h_ctl, E.h_frames, E.h_dec, E.h_status, E.h_chunks, E.h_items, E.h_pitems};
@@ -461,6 +464,7 @@ int device_init(Device &D) {
     D.front_fold = env_int("ATSC_FRONT_FOLD", 1, 0, 1) != 0;
     D.front_poly = env_int("ATSC_FRONT_POLY", 1, 0, 1) != 0;
     D.poly_items = env_int("ATSC_POLY_ITEMS", 1, 0, 1) != 0;
+    D.poly1_static = env_int("ATSC_POLY1_STATIC", 1, 0, 1) != 0;
     D.probe_kernel = env_int("ATSC_PROBE_KERNEL", 1, 0, 1) != 0;
     D.sms = sms;
     if ((rc = engine_init(D, D.eng[0], sms))) return rc;  // the others are set up when a call first needs them
@@ -579,7 +583,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     }
     // frames whose first Polynomial step k_poly1 evaluates in balanced work items (poly.cuh)
     auto poly1_frame = [&](const FrameReq &r) {
-        return D.poly_items && r.len >= POLY_ITEM_MIN_LEN && r.bounded && !r.select_only &&
+        return D.poly_items && r.len >= POLY_ITEM_MIN_LEN && poly_first_step(r.len) == P1_STEP && r.bounded && !r.select_only &&
                (r.comp == C_POLY || (r.comp == C_AUTO && (r.forced == 0xFF || r.forced == C_POLY)));
     };
     // (only when big frames are scarce: with several frames per CTA slot whole-frame items balance by themselves
@@ -595,7 +599,11 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     hcap = E.pitems_cap;
     if ((rc = grow(D, E.st, E.d_pitems, E.pitems_cap, n_pitems))) return rc;
     if ((rc = grow(D, E.st, E.h_pitems, hcap, E.pitems_cap, true))) return rc;
-    if ((rc = grow(D, E.st, E.d_ppart, E.ppart_cap, n_pitems))) return rc;
+    if ((rc = grow(D, E.st, E.d_ppart, E.ppart_cap, n_pitems * (D.poly1_static ? (size_t)P1_PARTS : 1u)))) return rc;
+    if (D.poly1_static) {
+        if ((rc = grow(D, E.st, E.d_p1list, E.p1list_cap, n_pitems))) return rc;
+        if ((rc = grow(D, E.st, E.d_p1kt, E.p1kt_cap, n_pitems * (size_t)POLY_ITEM_KEYS))) return rc;
+    }
     hcap = E.chunks_cap;
     if ((rc = grow(D, E.st, E.d_chunks, E.chunks_cap, n_chunks + n_sf))) return rc;
     if ((rc = grow(D, E.st, E.h_chunks, hcap, E.chunks_cap, true))) return rc;
@@ -708,10 +716,15 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     CK(cudaEventRecord(E.ev[1], st));
     launch_plan(E.d_frames, n, d_samples, E.d_parts, D.geoms_dev, st);
     if (n_pitems) {
-        launch_poly1(E.d_frames, E.d_pitems, (uint32_t)n_pitems, d_samples, E.d_ppart, E.queues + 11, st);
-        D.launches++;
+        if (D.poly1_static) {
+            launch_poly1s(E.d_frames, E.d_pitems, (uint32_t)n_pitems, d_samples, E.d_p1list, E.d_p1kt, E.d_ppart, E.queues + 11, st);
+            D.launches += 2;
+        } else {
+            launch_poly1(E.d_frames, E.d_pitems, (uint32_t)n_pitems, d_samples, E.d_ppart, E.queues + 11, st);
+            D.launches++;
+        }
     }
-    launch_poly(E.d_frames, n, d_samples, max_err, D.inv_d2, E.pool, E.d_ppart, E.queues + 1, st);
+    launch_poly(E.d_frames, n, d_samples, max_err, D.inv_d2, E.pool, E.d_ppart, D.poly1_static ? P1_PARTS : 1u, E.queues + 1, st);
     CK(cudaEventRecord(E.ev[2], st));
     if (any_small) {
         launch_fft_small(E.d_frames, n, d_samples, max_err, D.geoms_dev, E.d_arena, small_lmax, E.queues + 8, st);

@@ -32,6 +32,28 @@ constexpr uint8_t FRES_SURVIVOR = 4;
 constexpr uint32_t POLY_ITEM = 32768;          // samples per item
 constexpr uint32_t POLY_ITEM_MIN_LEN = 65536;  // frames this long go through k_poly1 (step 100, >= 2 items)
 __host__ __device__ inline uint32_t poly_item_count(uint32_t N) { return (N + POLY_ITEM - 1) / POLY_ITEM; }
+// the step Polynomial::compress_bounded tries first
+__host__ __device__ inline uint32_t poly_first_step(uint32_t N) {
+    const uint32_t baseline = (3 >= N / 100) ? 3 : N / 100;  // polynomial.rs:218-221
+    const uint32_t step = N / baseline;
+    return step < 1 ? 1 : step;
+}
+constexpr uint32_t POLY_ITEM_KEYS = 352;       // keys / tangents of one item (<= 82 blocks of 4 segments + the tail)
+// k_poly1_prep / k_poly1s (poly.cuh)
+constexpr uint32_t P1_STEP = 100;
+constexpr int P1_T = 512;                           // threads of k_poly1s: five groups of 100
+constexpr uint32_t P1_G = P1_T / P1_STEP;           // groups
+constexpr uint32_t P1_PARTS = P1_T / 32 + 1;        // partial sums per item: one per warp + k_poly1_prep's
+struct alignas(16) P1Item {
+    const double *d;       // the frame's samples
+    double vmin, vmax;
+    uint32_t b_lo, b_hi;   // NS-blocks of the item: segments 1 + NS * b_lo .. NS * b_hi
+    uint32_t out;          // parts[out * P1_PARTS + w]
+    uint32_t nkeys;        // keys 1 + NS * b_lo .. of the item (value, tangent) at kt_arena[kt ..]
+    uint64_t kt;
+    uint32_t tame, pad[3];
+};
+static_assert(sizeof(P1Item) == 64, "P1Item is copied as four 16-byte pieces");
 
 // One record per frame, lives in device memory for the duration of a wave.
 struct FrameWork {

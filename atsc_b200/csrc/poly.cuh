@@ -278,12 +278,6 @@ __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys 
 // [nblk * q / Q, nblk * (q + 1) / Q) of the step poly_frame tries first, the last item also the left-over segments
 // and the Linear ends; its tangents live in shared memory.  The MAPE is a sum: the items' partial sums are added
 // in item order by poly_frame, which goes on from there exactly as if it had evaluated the step itself.
-constexpr uint32_t POLY_ITEM_KEYS = 352;       // tangents of one item (<= 82 blocks of 4 segments + the tail)
-__host__ __device__ inline uint32_t poly_first_step(uint32_t N) {
-    const uint32_t baseline = (3 >= N / 100) ? 3 : N / 100;  // polynomial.rs:218-221
-    const uint32_t step = N / baseline;
-    return step < 1 ? 1 : step;
-}
 template <bool TAME>
 __device__ inline void poly_first_step_item(const double *__restrict__ d, uint32_t N, double vmin, double vmax, uint32_t q,
                                             double *part_out, double *tang_sm, double *scratch) {
@@ -304,6 +298,78 @@ __device__ inline void poly_first_step_item(const double *__restrict__ d, uint32
     const double s = block_sum(acc, scratch);
     if (t == 0) *part_out = s;
     __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_poly1s (default) + k_poly1_prep: the same first step without the per-item latency chain.
+//
+// ncu on the item kernel above (profiles/r2_p1_plain_vs_ring.md): 45 % of the warp-stall samples sit OUTSIDE the
+// segment loop -- queue atomic -> item -> frame record -> keys -> tangents -> barrier, then block_sum -- a chain of
+// four dependent global accesses per 32768-sample item; staging the samples through cp.async rings alone removed
+// the loop's long-scoreboard stalls (5.7 -> 1.3 per issue) and not one microsecond of the kernel's time.  So:
+//   * k_poly1_prep (one small CTA per candidate item) does everything that needs the frame record: it drops the
+//     items of frames that need no Polynomial candidate, writes (key, tangent) pairs of the item to an arena,
+//     evaluates the few samples the four-segment loop does not cover (left-over segments, Linear ends) and
+//     appends a 64-byte self-contained descriptor to a compacted list;
+//   * k_poly1s walks that list with a STATIC schedule (CTA b takes entries b, b + grid, ...: the entries are all
+//     ~32768 samples), so nothing on an item's path is a dependent global access: descriptors arrive two items
+//     ahead and the next item's keys one item ahead by cp.async, the samples through per-thread cp.async rings
+//     that run ACROSS item boundaries (a thread only ever reads back what it copied itself: cp.async.wait_group
+//     is the whole synchronisation inside the loop), and the result leaves as one partial sum per warp (no
+//     block-wide reduction).  One __syncthreads per item.
+// poly_frame adds a frame's P1_PARTS partial sums per item in a fixed order (block_sum over <= 68 values).
+// step is 100 for every frame of >= 10000 samples: N / (N / 100) = 100 + floor((N mod 100) / (N / 100)).
+// (P1_STEP, P1_T, P1_D, P1_G, P1_PARTS and the P1Item descriptor live in common.cuh: the host sizes arenas by them)
+struct P1Smem {
+    double2 kt[2][POLY_ITEM_KEYS];  // (key value, tangent) of the current / the next item
+    P1Item desc[4];                 // descriptors of the items k-1 .. k+2 of this CTA
+};
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+}
+// this thread's NS samples of the trip that starts at p (one per segment of the block)
+__device__ __forceinline__ void p1_load_trip(double (&o)[POLY_NS], const double *__restrict__ p) {
+#pragma unroll
+    for (int u = 0; u < POLY_NS; u++) o[u] = __ldg(p + (uint32_t)u * P1_STEP);
+}
+// The segment loop of one item for one thread (offset j of group g); returns its share of the MAPE sum.
+// o_nxt holds the samples of the item's first trip on entry (loaded while the previous item finished) and is
+// refilled one trip ahead inside the loop: the FP64 work of a trip covers the latency of the next trip's loads.
+template <bool TAME>
+__device__ __forceinline__ double p1_item_loop(const P1Item &I, const double2 *kp, double (&o_nxt)[POLY_NS], bool active,
+                                               uint32_t g, uint32_t j, double h00, double h10, double h01, double h11) {
+    constexpr int NS = POLY_NS;
+    const double vmin = I.vmin, vmax = I.vmax;
+    const uint32_t b_hi = I.b_hi;
+    const double *po = I.d + (size_t)(1u + NS * (I.b_lo + g)) * P1_STEP + j;  // this thread's samples of the current trip
+    double acc = 0.0;
+    // (the lanes beyond the fifth group make no trip but stay on the same path: barriers and shuffles are warp-wide)
+    for (uint32_t qq = active ? I.b_lo + g : b_hi; qq < b_hi; qq += P1_G) {
+        double o[NS], e[NS];
+        double2 kv[NS + 1];
+#pragma unroll
+        for (int u = 0; u < NS; u++) o[u] = o_nxt[u];
+        po += (size_t)NS * P1_G * P1_STEP;
+        if (qq + P1_G < b_hi) p1_load_trip(o_nxt, po);
+#pragma unroll
+        for (int u = 0; u <= NS; u++) kv[u] = kp[u];
+#pragma unroll
+        for (int u = 0; u < NS; u++) {
+            const double v = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(kv[u].x, h00), __dmul_rn(kv[u].y, h10)), __dmul_rn(kv[u + 1].x, h01)),
+                                       __dmul_rn(kv[u + 1].y, h11));
+            e[u] = TAME ? mape_term_tame(round_and_limit5_tame(v, vmin, vmax), o[u]) : mape_term(round_and_limit5_fast(v, vmin, vmax), o[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < NS; u++) acc += e[u];
+        kp += NS * P1_G;
+    }
+    return acc;
 }
 
 // Polynomial::polynomial_to_data (polynomial.rs:342-373) + round_and_limit_f64 for a whole frame:
@@ -434,7 +500,7 @@ __device__ inline bool poly_loop_near_tie(double cur, double target) {
 // Writes poly_* fields of fw (thread 0).  `sh` = shared scratch (>= 40 doubles).
 __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, double max_err,
                                   const double *__restrict__ inv_d2, double *sh, PolyWs ws,
-                                  const double *__restrict__ first_parts) {
+                                  const double *__restrict__ first_parts, uint32_t parts_per_item) {
     const uint32_t N = fw->len;
     const double vmin = fw->vmin, vmax = fw->vmax;
     const int ptype = fw->poly_type;
@@ -470,9 +536,17 @@ __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, d
                 } else if (it == 1 && (fw->front_res & FRES_POLY1) && step == fw->poly_step) {
                     cur = fw->poly_err;  // k_front evaluated this step while it streamed the frame
                 } else if (it == 1 && fw->poly_parts && ptype == 0) {
-                    // k_poly1 evaluated this step in poly_parts work items: add their sums in item order
+                    // k_poly1 / k_poly1s evaluated this step in poly_parts work items: add their partial sums in a
+                    // fixed order (one per item, or -- k_poly1s -- one per warp of each item plus k_poly1_prep's)
                     double sum = 0.0;
-                    for (uint32_t q = 0; q < fw->poly_parts; q++) sum += first_parts[fw->poly_part0 + q];
+                    if (parts_per_item == 1u) {
+                        for (uint32_t q = 0; q < fw->poly_parts; q++) sum += first_parts[fw->poly_part0 + q];
+                    } else {
+                        const uint32_t np = fw->poly_parts * parts_per_item;  // <= 4 * 17
+                        double mine = 0.0;
+                        for (uint32_t e = threadIdx.x; e < np; e += blockDim.x) mine += first_parts[(size_t)fw->poly_part0 * parts_per_item + e];
+                        sum = block_sum(mine, sh);
+                    }
                     cur = __ddiv_rn(sum, (double)N);
                 } else {
                     cur = tame ? poly_mape<true>(d, k, ptype, vmin, vmax, inv_d2, ws, sh)

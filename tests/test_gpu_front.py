@@ -238,6 +238,48 @@ def test_poly_items_match_whole_frames(poly_item_ctxs, comp, err):
                 assert b == O.compress_bounded(comp, a, np.float32(err))[0], name
 
 
+def test_poly1_static_matches_items():
+    """k_poly1_prep + k_poly1s (compacted self-contained item list, static schedule, samples through per-thread
+    cp.async rings that run across item boundaries, one partial sum per warp) against the queue-driven k_poly1
+    (ATSC_POLY1_STATIC=0): same per-sample arithmetic, another summation tree -- same records and payload bytes,
+    errors equal to 1e-12 relative; non-tame frames (zeros, sign changes, NaN), constant frames between the big
+    ones (dropped by the prep kernel) and lengths that move the item boundaries included; vs the oracle too."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import atsc_b200
+    made = []
+    for v in ("1", "0"):
+        os.environ["ATSC_POLY1_STATIC"] = v
+        try:
+            made.append(atsc_b200.Context())
+        finally:
+            os.environ.pop("ATSC_POLY1_STATIC")
+    try:
+        rng = np.random.default_rng(5)
+        cs = [c for c in front_frames() if len(c[1]) >= 65536]
+        for n in (65536, 65537, 70001, 98304, 99999, 131071, 131072):
+            cs.append((f"util{n}", gen.make("util", n, n)))
+            cs.append((f"const{n}", np.full(n, 3.25)))
+            cs.append((f"sign{n}", np.sin(np.arange(n) / 900.0) * 3.0 + rng.normal(0, 0.01, n)))  # not tame
+        # enough items that every CTA of k_poly1s walks several (descriptor / key double buffering, ring hand-over)
+        for i in range(12):
+            cs.append((f"periodic131072_{i}", gen.make("periodic", 131072, 100 + i)))
+        arrays = [a for _, a in cs]
+        names = [n for n, _ in cs]
+        for comp, err in ((O.AUTO, 0.05), (O.POLYNOMIAL, 0.05), (O.POLYNOMIAL, 0.002), (O.POLYNOMIAL, 0.0)):
+            r_on = run_batch(made[0], arrays, comp, max_error=err)
+            r_off = run_batch(made[1], arrays, comp, max_error=err)
+            same_records(r_on, r_off, names, f"poly1 static {O.NAMES[comp]} e={err}")
+            if comp == O.POLYNOMIAL:
+                for (name, a), (o, b) in zip(cs, r_on):
+                    if not o.near_tie and not name.startswith("nan"):
+                        assert b == O.compress_bounded(comp, a, np.float32(err))[0], name
+    finally:
+        for c in made:
+            c.close()
+
+
 def test_probe_kernel_matches_in_kernel_probe():
     """k_probe (small probe tails, decided frames skip k_fft_fwd's probe) against ATSC_PROBE_KERNEL=0."""
     import torch
