@@ -78,9 +78,8 @@ struct Engine {
     std::vector<uint8_t> fronted;  // issue_wave scratch
     ChunkRef *d_pitems = nullptr, *h_pitems = nullptr;  // k_poly1 work items (frame, part)
     double *d_ppart = nullptr;                          // their partial MAPE sums (P1_PARTS per item with k_poly1s)
-    P1Item *d_p1list = nullptr;                         // k_poly1_prep's compacted descriptors for k_poly1s
-    double2 *d_p1kt = nullptr;                          // ... and (key, tangent) pairs, POLY_ITEM_KEYS per item
-    size_t pitems_cap = 0, ppart_cap = 0, p1list_cap = 0, p1kt_cap = 0;
+    P1Item *d_p1list = nullptr;                         // k_plan's compacted item descriptors for k_poly1s
+    size_t pitems_cap = 0, ppart_cap = 0, p1list_cap = 0;
     float2 *d_spec_xd = nullptr;  // per-frame half spectra of the wave (k_fft_fwd -> k_fft)
     uint32_t *d_spec_keys = nullptr;
     size_t spec_xd_cap = 0, spec_keys_cap = 0;
@@ -376,7 +375,7 @@ void engine_free(Engine &E) {
                     P.fft_locD, P.fft_locM, P.fft_ovr, P.fft_cD, P.fft_cM, P.fft_dlist, P.poly_slope, P.dec_pts,
                     P.dec_mark, P.dec_idx, E.queues, E.d_ctl, E.d_frames, E.d_samples, E.d_arena, E.d_payload,
                     E.d_dec, E.d_pay_in, E.d_out, E.d_status, E.d_spec_xd, E.d_spec_keys, E.d_chunks, E.d_parts,
-                    E.d_items, E.d_fold, E.d_pitems, E.d_ppart, E.d_p1list, E.d_p1kt};
+                    E.d_items, E.d_fold, E.d_pitems, E.d_ppart, E.d_p1list};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     void *hp[] = {E.h_ctl, E.h_frames, E.h_dec, E.h_status, E.h_chunks, E.h_items, E.h_pitems};
@@ -600,10 +599,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     if ((rc = grow(D, E.st, E.d_pitems, E.pitems_cap, n_pitems))) return rc;
     if ((rc = grow(D, E.st, E.h_pitems, hcap, E.pitems_cap, true))) return rc;
     if ((rc = grow(D, E.st, E.d_ppart, E.ppart_cap, n_pitems * (D.poly1_static ? (size_t)P1_PARTS : 1u)))) return rc;
-    if (D.poly1_static) {
-        if ((rc = grow(D, E.st, E.d_p1list, E.p1list_cap, n_pitems))) return rc;
-        if ((rc = grow(D, E.st, E.d_p1kt, E.p1kt_cap, n_pitems * (size_t)POLY_ITEM_KEYS))) return rc;
-    }
+    if (D.poly1_static && (rc = grow(D, E.st, E.d_p1list, E.p1list_cap, n_pitems))) return rc;
     hcap = E.chunks_cap;
     if ((rc = grow(D, E.st, E.d_chunks, E.chunks_cap, n_chunks + n_sf))) return rc;
     if ((rc = grow(D, E.st, E.h_chunks, hcap, E.chunks_cap, true))) return rc;
@@ -695,7 +691,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
     CK(cudaMemcpyAsync(E.d_frames, E.h_frames, (size_t)n * sizeof(FrameWork), cudaMemcpyHostToDevice, st));
     if (n_chunks + n_sf) CK(cudaMemcpyAsync(E.d_chunks, E.h_chunks, (n_chunks + n_sf) * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
     if (n_items) CK(cudaMemcpyAsync(E.d_items, E.h_items, n_items * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    if (n_pitems) CK(cudaMemcpyAsync(E.d_pitems, E.h_pitems, n_pitems * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
+    if (n_pitems && !D.poly1_static) CK(cudaMemcpyAsync(E.d_pitems, E.h_pitems, n_pitems * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(E.queues, 0, 64 * sizeof(unsigned), st));
     CK(cudaMemsetAsync(E.d_ctl, 0, sizeof(WaveCtl), st));
     CK(cudaEventRecord(E.ev[12], st));
@@ -714,11 +710,12 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
         D.launches++;
     }
     CK(cudaEventRecord(E.ev[1], st));
-    launch_plan(E.d_frames, n, d_samples, E.d_parts, D.geoms_dev, st);
+    const bool p1s = n_pitems && D.poly1_static;
+    launch_plan(E.d_frames, n, d_samples, E.d_parts, D.geoms_dev, p1s ? E.d_p1list : nullptr, E.queues + 11, st);
     if (n_pitems) {
-        if (D.poly1_static) {
-            launch_poly1s(E.d_frames, E.d_pitems, (uint32_t)n_pitems, d_samples, E.d_p1list, E.d_p1kt, E.d_ppart, E.queues + 11, st);
-            D.launches += 2;
+        if (p1s) {
+            launch_poly1s(E.d_p1list, E.queues + 11, (uint32_t)n_pitems, E.d_ppart, st);
+            D.launches++;
         } else {
             launch_poly1(E.d_frames, E.d_pitems, (uint32_t)n_pitems, d_samples, E.d_ppart, E.queues + 11, st);
             D.launches++;

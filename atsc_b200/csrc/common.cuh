@@ -39,19 +39,19 @@ __host__ __device__ inline uint32_t poly_first_step(uint32_t N) {
     return step < 1 ? 1 : step;
 }
 constexpr uint32_t POLY_ITEM_KEYS = 352;       // keys / tangents of one item (<= 82 blocks of 4 segments + the tail)
-// k_poly1_prep / k_poly1s (poly.cuh)
+// k_poly1s (poly.cuh): self-contained descriptors of its work items, appended by k_plan
 constexpr uint32_t P1_STEP = 100;
 constexpr int P1_T = 512;                           // threads of k_poly1s: five groups of 100
 constexpr uint32_t P1_G = P1_T / P1_STEP;           // groups
-constexpr uint32_t P1_PARTS = P1_T / 32 + 1;        // partial sums per item: one per warp + k_poly1_prep's
+constexpr uint32_t P1_PARTS = P1_T / 32;            // partial sums per item: one per warp
 struct alignas(16) P1Item {
     const double *d;       // the frame's samples
     double vmin, vmax;
+    uint32_t N;            // frame length
     uint32_t b_lo, b_hi;   // NS-blocks of the item: segments 1 + NS * b_lo .. NS * b_hi
-    uint32_t out;          // parts[out * P1_PARTS + w]
-    uint32_t nkeys;        // keys 1 + NS * b_lo .. of the item (value, tangent) at kt_arena[kt ..]
-    uint64_t kt;
-    uint32_t tame, pad[3];
+    uint32_t out;          // parts[out * P1_PARTS + warp]
+    uint32_t nkeys;        // keys 1 + NS * b_lo .. NS * b_hi + 1 of the item
+    uint32_t tame, pad[4];
 };
 static_assert(sizeof(P1Item) == 64, "P1Item is copied as four 16-byte pieces");
 

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256, 8) k_stats(const FrameWork *__restrict__ 
 // per frame: combine the chunk partials into the stats, then decide which candidates run
 // (frame/mod.rs:71-149, compressor/mod.rs:63-107)
 __global__ void k_plan(FrameWork *fr, uint32_t n, const double *__restrict__ samples, const StatsPart *__restrict__ parts,
-                       const FftGeom *__restrict__ geoms) {
+                       const FftGeom *__restrict__ geoms, P1Item *__restrict__ p1_list, unsigned *p1_count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     FrameWork *fw = &fr[i];
@@ -71,6 +71,28 @@ __global__ void k_plan(FrameWork *fr, uint32_t n, const double *__restrict__ sam
     const uint32_t nparts = (fw->front_mode & FM_SFOLD) ? sfold_items(geoms[fw->geom].M1) : (fw->len + STATS_CHUNK - 1) / STATS_CHUNK;
     finish_stats(samples + fw->off, fw->len, parts + fw->chunk0, nparts, fw);
     plan_frame(fw);
+    // k_poly1s' work items: the frames poly_frame would evaluate the first step for (bounded Catmull-Rom, not
+    // "same max and min"), cut into poly_parts balanced ranges of four-segment blocks (poly.cuh)
+    if (p1_list && fw->poly_parts && fw->need_poly && !fw->poly_type && !fw->poly_valid && fw->bounded && fw->vmax != fw->vmin) {
+        const uint32_t N = fw->len, Q = fw->poly_parts;
+        const PolyKeys k = poly_keys(N, P1_STEP);  // poly_first_step(N) == 100: the host lists no other frame
+        const uint32_t nblk = (k.K - 3) / POLY_NS;
+        const unsigned slot0 = atomicAdd(p1_count, Q);
+        for (uint32_t q = 0; q < Q; q++) {
+            P1Item I;
+            I.d = samples + fw->off;
+            I.vmin = fw->vmin;
+            I.vmax = fw->vmax;
+            I.N = N;
+            I.b_lo = (uint32_t)((uint64_t)nblk * q / Q);
+            I.b_hi = (uint32_t)((uint64_t)nblk * (q + 1) / Q);
+            I.out = fw->poly_part0 + q;
+            I.nkeys = POLY_NS * (I.b_hi - I.b_lo) + 1;
+            I.tame = poly_tame(fw->vmin, fw->vmax) ? 1u : 0u;
+            I.pad[0] = I.pad[1] = I.pad[2] = I.pad[3] = 0u;
+            p1_list[slot0 + q] = I;
+        }
+    }
 }
 
 // Fused front end of the big frames (front.cuh): stats + first Polynomial step + FFT probe fold in
@@ -137,69 +159,9 @@ __global__ void __launch_bounds__(512, 2) k_poly1(const FrameWork *__restrict__ 
     }
 }
 
-// k_poly1_prep + k_poly1s: the same step with a compacted, self-contained item list and a static schedule
-// (poly.cuh).  One CTA per candidate item: keys + tangents to the arena, the samples outside the four-segment
-// blocks (left-over segments, Linear ends) evaluated here, one descriptor appended for k_poly1s.
-__global__ void __launch_bounds__(128) k_poly1_prep(const FrameWork *__restrict__ fr, const ChunkRef *__restrict__ items,
-                                                    uint32_t n_items, const double *__restrict__ samples,
-                                                    P1Item *__restrict__ out_items, unsigned *count,
-                                                    double2 *__restrict__ kt_arena, double *__restrict__ parts) {
-    __shared__ double shd[64];
-    const uint32_t it = blockIdx.x, t = threadIdx.x, T = blockDim.x;
-    if (it >= n_items) return;
-    const ChunkRef ref = items[it];
-    const FrameWork *fw = &fr[ref.frame];
-    // the frames poly_frame would evaluate this step for (bounded Catmull-Rom, not "same max and min")
-    if (!fw->need_poly || fw->poly_type || fw->poly_valid || !fw->bounded || fw->vmax == fw->vmin) return;
-    const double *d = samples + fw->off;
-    const uint32_t N = fw->len, q = ref.start;
-    const double vmin = fw->vmin, vmax = fw->vmax;
-    const PolyKeys k = poly_keys(N, P1_STEP);  // poly_first_step(N) == 100: the host lists no other frame
-    const uint32_t K = k.K, Q = poly_item_count(N), nblk = (K - 3) / POLY_NS;
-    const uint32_t b_lo = (uint32_t)((uint64_t)nblk * q / Q), b_hi = (uint32_t)((uint64_t)nblk * (q + 1) / Q);
-    const bool tail = q + 1 == Q;
-    const uint32_t j_lo = 1 + POLY_NS * b_lo, j_hi = POLY_NS * b_hi + 1;  // keys of the blocks' segments
-    const size_t kbase = (size_t)it * POLY_ITEM_KEYS;
-    const double stepd = (double)P1_STEP;
-    for (uint32_t jj = j_lo + t; jj <= j_hi; jj += T) {
-        const uint32_t pa = poly_pos(k, jj - 1), pb = poly_pos(k, jj + 1);
-        kt_arena[kbase + jj - j_lo] = make_double2(
-            d[poly_pos(k, jj)], __dmul_rn(__ddiv_rn(__dsub_rn(d[pb], d[pa]), __dsub_rn((double)pb, (double)pa)), stepd));
-    }
-    double acc = 0.0;
-    if (tail) {
-        // Catmull-Rom segments behind the last whole block (fewer than NS) through the per-sample arithmetic,
-        // which yields the same values as the segment loop (poly_mape), then the Linear ends
-        auto pts = [&](uint32_t jx) { return d[poly_pos(k, jx)]; };
-        const uint32_t i0 = nblk * POLY_NS + 1, i_hi = K - 3;
-        const uint32_t nleft = i_hi >= i0 ? (i_hi - i0 + 1) * P1_STEP : 0u;
-        for (uint32_t e = t; e < nleft; e += T) {
-            const uint32_t x = i0 * P1_STEP + e;
-            acc += mape_term(round_and_limit5_fast(poly_eval_at(k, x, pts), vmin, vmax), d[x]);
-        }
-        acc += poly_mape_ends(d, k, vmin, vmax);
-    }
-    const double s = block_sum(acc, shd);
-    if (t == 0) {
-        const uint32_t out = fw->poly_part0 + q;
-        parts[(size_t)out * P1_PARTS + (P1_PARTS - 1)] = s;
-        P1Item I;
-        I.d = d;
-        I.vmin = vmin;
-        I.vmax = vmax;
-        I.b_lo = b_lo;
-        I.b_hi = b_hi;
-        I.out = out;
-        I.nkeys = j_hi - j_lo + 1;
-        I.kt = kbase;
-        I.tame = poly_tame(vmin, vmax) ? 1u : 0u;
-        I.pad[0] = I.pad[1] = I.pad[2] = 0u;
-        out_items[atomicAdd(count, 1u)] = I;
-    }
-}
-
+// the same step from k_plan's compacted, self-contained item list with a static schedule (poly.cuh)
 __global__ void __launch_bounds__(P1_T, 2) k_poly1s(const P1Item *__restrict__ items, const unsigned *__restrict__ count,
-                                                   const double2 *__restrict__ kt_arena, double *__restrict__ parts) {
+                                                   double *__restrict__ parts) {
     __shared__ P1Smem sm_;
     P1Smem *sm = &sm_;
     const uint32_t t = threadIdx.x, nb = gridDim.x, first = blockIdx.x;
@@ -208,14 +170,22 @@ __global__ void __launch_bounds__(P1_T, 2) k_poly1s(const P1Item *__restrict__ i
     const uint32_t n_mine = (n_valid - first + nb - 1) / nb;  // entries first, first + nb, ...
     const uint32_t g = t / P1_STEP, j = t - g * P1_STEP;
     const bool active = g < P1_G;
-    // ---- start-up: descriptors of the first two items, keys of the first, samples of the first trip
+    // raw keys j_lo - 1 .. j_hi + 1 of item kk into raw[kk & 1] (its descriptor is visible), one 8-byte copy per thread
+    auto fetch_keys = [&](uint32_t kk) {
+        const P1Item &X = sm->desc[kk & 3u];
+        if (t < X.nkeys + 2u) {
+            const uint32_t jj = POLY_NS * X.b_lo + t, kreg = (X.N + P1_STEP - 1u) / P1_STEP;  // key j_lo - 1 + t
+            cp_async_8(&sm->raw[kk & 1u][t], X.d + (jj < kreg ? jj * P1_STEP : X.N - 1u));
+        }
+    };
+    // ---- start-up: descriptors of the first two items, raw keys of the first, samples of the first trip
     if (t < 8u && (t >> 2) < n_mine)
         cp_async_16(reinterpret_cast<char *>(&sm->desc[t >> 2]) + (t & 3u) * 16u,
                     reinterpret_cast<const char *>(&items[first + (t >> 2) * nb]) + (t & 3u) * 16u);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    if (t < sm->desc[0].nkeys) cp_async_16(&sm->kt[0][t], kt_arena + sm->desc[0].kt + t);
+    fetch_keys(0u);
     cp_async_commit();
     double o_nxt[POLY_NS] = {0.0, 0.0, 0.0, 0.0};
     if (active) p1_load_trip(o_nxt, sm->desc[0].d + (size_t)(1u + POLY_NS * (sm->desc[0].b_lo + g)) * P1_STEP + j);
@@ -227,21 +197,26 @@ __global__ void __launch_bounds__(P1_T, 2) k_poly1s(const P1Item *__restrict__ i
     const double h00 = __dadd_rn(__dsub_rn(two_t3, three_t2), 1.0), h10 = __dadd_rn(__dsub_rn(t3, two_t2), tt);
     const double h01 = __dsub_rn(three_t2, two_t3), h11 = __dsub_rn(t3, t2);
     for (uint32_t k = 0; k < n_mine; k++) {
-        cp_async_wait<0>();  // this thread's copies of item k's keys / descriptor k+1 (issued one item ago, or above)
-        __syncthreads();     // everybody is done with item k-1; desc[k], desc[k+1] and kt[k & 1] are visible
+        const P1Item &I = sm->desc[k & 3u];
+        cp_async_wait<0>();  // this thread's copies of item k's raw keys / descriptor k+1 (issued one item ago, or above)
+        __syncthreads();     // everybody is done with item k-1 (kt is free); desc[k], desc[k+1], raw[k & 1] are visible
+        if (t < I.nkeys) {
+            // tangent of key jj = j_lo + t (poly_mape's pre-pass): (v[jj+1] - v[jj-1]) / (pos[jj+1] - pos[jj-1]) * step
+            const uint32_t jj = 1u + POLY_NS * I.b_lo + t, kreg = (I.N + P1_STEP - 1u) / P1_STEP;
+            const uint32_t pa = (jj - 1u) * P1_STEP, pb = jj + 1u < kreg ? (jj + 1u) * P1_STEP : I.N - 1u;
+            const double *r = sm->raw[k & 1u] + t;
+            sm->kt[t] = make_double2(r[1], __dmul_rn(__ddiv_rn(__dsub_rn(r[2], r[0]), __dsub_rn((double)pb, (double)pa)), (double)P1_STEP));
+        }
+        __syncthreads();
         if (k + 2u < n_mine && t < 4u)
             cp_async_16(reinterpret_cast<char *>(&sm->desc[(k + 2u) & 3u]) + t * 16u,
                         reinterpret_cast<const char *>(&items[first + (k + 2u) * nb]) + t * 16u);
-        if (k + 1u < n_mine) {
-            const P1Item &Nx = sm->desc[(k + 1u) & 3u];
-            if (t < Nx.nkeys) cp_async_16(&sm->kt[(k + 1u) & 1u][t], kt_arena + Nx.kt + t);
-        }
+        if (k + 1u < n_mine) fetch_keys(k + 1u);
         cp_async_commit();
-        const P1Item &I = sm->desc[k & 3u];
-        const double2 *kp = sm->kt[k & 1u] + POLY_NS * g;  // key 1 + NS * (b_lo + g) of the item's first trip
+        const double2 *kp = sm->kt + POLY_NS * g;  // key 1 + NS * (b_lo + g) of the item's first trip
         double acc = I.tame ? p1_item_loop<true>(I, kp, o_nxt, active, g, j, h00, h10, h01, h11)
                             : p1_item_loop<false>(I, kp, o_nxt, active, g, j, h00, h10, h01, h11);
-        if (k + 1u < n_mine && active) {  // the next item's first trip, in flight across the reduction and the barrier
+        if (k + 1u < n_mine && active) {  // the next item's first trip, in flight across the reduction and the barriers
             const P1Item &Nx = sm->desc[(k + 1u) & 3u];
             p1_load_trip(o_nxt, Nx.d + (size_t)(1u + POLY_NS * (Nx.b_lo + g)) * P1_STEP + j);
         }
@@ -1350,8 +1325,8 @@ void launch_stats(const FrameWork *fr, const ChunkRef *chunks, uint32_t n_chunks
     k_stats<<<grid_for(n_chunks, 8 * sms()), 256, 0, st>>>(fr, chunks, n_chunks, samples, parts, q);
 }
 void launch_plan(FrameWork *fr, uint32_t n, const double *samples, const StatsPart *parts, const FftGeom *geoms,
-                 cudaStream_t st) {
-    k_plan<<<(n + 63) / 64, 64, 0, st>>>(fr, n, samples, parts, geoms);
+                 P1Item *p1_list, unsigned *p1_count, cudaStream_t st) {
+    k_plan<<<(n + 63) / 64, 64, 0, st>>>(fr, n, samples, parts, geoms, p1_list, p1_count);
 }
 void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_err, const double *inv_d2,
                  SlotPool pool, const double *first_parts, uint32_t parts_per_item, unsigned *q, cudaStream_t st) {
@@ -1361,10 +1336,8 @@ void launch_poly1(const FrameWork *fr, const ChunkRef *items, uint32_t n_items, 
                   unsigned *q, cudaStream_t st) {
     k_poly1<<<grid_for(n_items, 2 * sms()), 512, 0, st>>>(fr, items, n_items, samples, parts, q);
 }
-void launch_poly1s(const FrameWork *fr, const ChunkRef *items, uint32_t n_items, const double *samples, P1Item *list,
-                   double2 *kt_arena, double *parts, unsigned *count, cudaStream_t st) {
-    k_poly1_prep<<<n_items, 128, 0, st>>>(fr, items, n_items, samples, list, count, kt_arena, parts);
-    k_poly1s<<<grid_for(n_items, 2 * sms()), P1_T, 0, st>>>(list, count, kt_arena, parts);
+void launch_poly1s(const P1Item *list, const unsigned *count, uint32_t n_items, double *parts, cudaStream_t st) {
+    k_poly1s<<<grid_for(n_items, 2 * sms()), P1_T, 0, st>>>(list, count, parts);
 }
 void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err, SlotPool pool, unsigned *q,
                 cudaStream_t st) {

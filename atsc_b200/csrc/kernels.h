@@ -45,15 +45,15 @@ struct DecFrame {
 // compress pipeline; q = device array of >= 8 zeroed uint32 work-queue counters
 void launch_stats(const FrameWork *fr, const ChunkRef *chunks, uint32_t n_chunks, const double *samples, StatsPart *parts,
                   unsigned *q, cudaStream_t st);
+// p1_list / p1_count: k_poly1s' item descriptors are appended here (null: none)
 void launch_plan(FrameWork *fr, uint32_t n, const double *samples, const StatsPart *parts, const FftGeom *geoms,
-                 cudaStream_t st);
+                 P1Item *p1_list, unsigned *p1_count, cudaStream_t st);
 void launch_poly(FrameWork *fr, uint32_t n, const double *samples, double max_err, const double *inv_d2,
                  SlotPool pool, const double *first_parts, uint32_t parts_per_item, unsigned *q, cudaStream_t st);
 // first candidate step of the frames with poly_parts != 0: items = (frame, part) pairs, one partial MAPE sum each
 void launch_poly1(const FrameWork *fr, const ChunkRef *items, uint32_t n_items, const double *samples, double *parts,
                   unsigned *q, cudaStream_t st);
-void launch_poly1s(const FrameWork *fr, const ChunkRef *items, uint32_t n_items, const double *samples, P1Item *list,
-                   double2 *kt_arena, double *parts, unsigned *count, cudaStream_t st);
+void launch_poly1s(const P1Item *list, const unsigned *count, uint32_t n_items, double *parts, cudaStream_t st);
 void launch_rle(FrameWork *fr, uint32_t n, const double *samples, double max_err, SlotPool pool,
                 unsigned *q, cudaStream_t st);
 void launch_fft(FrameWork *fr, uint32_t n, const double *samples, double max_err, const FftGeom *geoms,

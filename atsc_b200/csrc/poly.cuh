@@ -301,29 +301,33 @@ __device__ inline void poly_first_step_item(const double *__restrict__ d, uint32
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_poly1s (default) + k_poly1_prep: the same first step without the per-item latency chain.
+// k_poly1s (default): the same first step without the per-item latency chain.
 //
-// ncu on the item kernel above (profiles/r2_p1_plain_vs_ring.md): 45 % of the warp-stall samples sit OUTSIDE the
+// ncu on the item kernel above (profiles/r2_p1_variants.md): 45 % of the warp-stall samples sit OUTSIDE the
 // segment loop -- queue atomic -> item -> frame record -> keys -> tangents -> barrier, then block_sum -- a chain of
-// four dependent global accesses per 32768-sample item; staging the samples through cp.async rings alone removed
-// the loop's long-scoreboard stalls (5.7 -> 1.3 per issue) and not one microsecond of the kernel's time.  So:
-//   * k_poly1_prep (one small CTA per candidate item) does everything that needs the frame record: it drops the
-//     items of frames that need no Polynomial candidate, writes (key, tangent) pairs of the item to an arena,
-//     evaluates the few samples the four-segment loop does not cover (left-over segments, Linear ends) and
-//     appends a 64-byte self-contained descriptor to a compacted list;
+// four dependent global accesses per 32768-sample item.  Here nothing on an item's path is a dependent global access:
+//   * k_plan, which decides per frame whether the Polynomial candidate runs at all, appends one self-contained
+//     64-byte descriptor per work item to a compacted list (the items of constant frames never exist);
 //   * k_poly1s walks that list with a STATIC schedule (CTA b takes entries b, b + grid, ...: the entries are all
-//     ~32768 samples), so nothing on an item's path is a dependent global access: descriptors arrive two items
-//     ahead and the next item's keys one item ahead by cp.async, the samples through per-thread cp.async rings
-//     that run ACROSS item boundaries (a thread only ever reads back what it copied itself: cp.async.wait_group
-//     is the whole synchronisation inside the loop), and the result leaves as one partial sum per warp (no
-//     block-wide reduction).  One __syncthreads per item.
-// poly_frame adds a frame's P1_PARTS partial sums per item in a fixed order (block_sum over <= 68 values).
+//     ~32768 samples): descriptors arrive two items ahead and the next item's raw keys one item ahead by cp.async
+//     (their tangents are computed from shared memory at the item boundary), the samples one trip ahead in
+//     registers -- the first trip of the NEXT item included, loaded while the current item's sums are reduced --
+//     and the result leaves as one partial sum per warp (no block-wide reduction).  Two barriers per item.
+//   * the samples the four-segment blocks do not cover (left-over segments, Linear ends: ~300 per frame) are
+//     evaluated by poly_frame when it adds up the frame's partial sums (poly_first_step_rest).
+// Staging the samples through shared-memory cp.async rings instead (measured) removes every load stall and costs
+// 26 more instructions per trip -- and instructions are what this loop is short of: a B200 FP64 instruction holds
+// its scheduler's issue port for two cycles (tools/ubench/p1arith.cu), so a trip costs 2 * 76 + 63 cycles.
 // step is 100 for every frame of >= 10000 samples: N / (N / 100) = 100 + floor((N mod 100) / (N / 100)).
-// (P1_STEP, P1_T, P1_D, P1_G, P1_PARTS and the P1Item descriptor live in common.cuh: the host sizes arenas by them)
 struct P1Smem {
-    double2 kt[2][POLY_ITEM_KEYS];  // (key value, tangent) of the current / the next item
-    P1Item desc[4];                 // descriptors of the items k-1 .. k+2 of this CTA
+    double2 kt[POLY_ITEM_KEYS];          // (key value, tangent) of the current item's keys
+    double raw[2][POLY_ITEM_KEYS + 2];   // raw keys j_lo - 1 .. j_hi + 1 of the current / the next item
+    P1Item desc[4];                      // descriptors of the items k-1 .. k+2 of this CTA
 };
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                  : "memory");
@@ -370,6 +374,21 @@ __device__ __forceinline__ double p1_item_loop(const P1Item &I, const double2 *k
         kp += NS * P1_G;
     }
     return acc;
+}
+
+// The part of the first step's MAPE sum that k_poly1s' four-segment blocks do not cover: the Catmull-Rom segments
+// behind the last whole block (fewer than NS) through the per-sample arithmetic -- which yields the same values as
+// the segment loop (poly_mape) -- and the Linear ends.  Returns this thread's share; all threads call.
+__device__ inline double poly_first_step_rest(const double *__restrict__ d, const PolyKeys &k, double vmin, double vmax) {
+    auto pts = [&](uint32_t jx) { return d[poly_pos(k, jx)]; };
+    const uint32_t nblk = (k.K - 3) / POLY_NS, i0 = nblk * POLY_NS + 1, i_hi = k.K - 3;
+    const uint32_t nleft = i_hi >= i0 ? (i_hi - i0 + 1) * k.step : 0u;
+    double acc = 0.0;
+    for (uint32_t e = threadIdx.x; e < nleft; e += blockDim.x) {
+        const uint32_t x = i0 * k.step + e;
+        acc += mape_term(round_and_limit5_fast(poly_eval_at(k, x, pts), vmin, vmax), d[x]);
+    }
+    return acc + poly_mape_ends(d, k, vmin, vmax);
 }
 
 // Polynomial::polynomial_to_data (polynomial.rs:342-373) + round_and_limit_f64 for a whole frame:
@@ -537,13 +556,13 @@ __device__ inline void poly_frame(const double *__restrict__ d, FrameWork *fw, d
                     cur = fw->poly_err;  // k_front evaluated this step while it streamed the frame
                 } else if (it == 1 && fw->poly_parts && ptype == 0) {
                     // k_poly1 / k_poly1s evaluated this step in poly_parts work items: add their partial sums in a
-                    // fixed order (one per item, or -- k_poly1s -- one per warp of each item plus k_poly1_prep's)
+                    // fixed order (one per item, or -- k_poly1s -- one per warp of each item plus the samples its blocks leave out)
                     double sum = 0.0;
                     if (parts_per_item == 1u) {
                         for (uint32_t q = 0; q < fw->poly_parts; q++) sum += first_parts[fw->poly_part0 + q];
                     } else {
-                        const uint32_t np = fw->poly_parts * parts_per_item;  // <= 4 * 17
-                        double mine = 0.0;
+                        const uint32_t np = fw->poly_parts * parts_per_item;  // <= 4 * 16
+                        double mine = poly_first_step_rest(d, k, vmin, vmax);
                         for (uint32_t e = threadIdx.x; e < np; e += blockDim.x) mine += first_parts[(size_t)fw->poly_part0 * parts_per_item + e];
                         sum = block_sum(mine, sh);
                     }

@@ -69,7 +69,7 @@ def test_library_holds_sm100a_code_for_every_kernel():
         pytest.skip("cuobjdump not available")
     r = subprocess.run([cuobjdump, "-elf", atsc_b200.lib_path()], capture_output=True, text=True, timeout=300)
     assert "sm_100a" in r.stdout or "sm_100" in r.stdout
-    for k in ("k_stats", "k_sfold", "k_front", "k_plan", "k_poly1", "k_poly1_prep", "k_poly1s", "k_poly", "k_fft_small", "k_probe", "k_fft_fwd", "k_fft", "k_rle",
+    for k in ("k_stats", "k_sfold", "k_front", "k_plan", "k_poly1", "k_poly1s", "k_poly", "k_fft_small", "k_probe", "k_fft_fwd", "k_fft", "k_rle",
               "k_noop_size", "k_select", "k_scan", "k_emit", "k_decode"):
         assert f"atsc{len(k)}{k}" in r.stdout, k      # Itanium-mangled atsc::k_*
 

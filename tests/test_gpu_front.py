@@ -239,11 +239,12 @@ def test_poly_items_match_whole_frames(poly_item_ctxs, comp, err):
 
 
 def test_poly1_static_matches_items():
-    """k_poly1_prep + k_poly1s (compacted self-contained item list, static schedule, samples through per-thread
-    cp.async rings that run across item boundaries, one partial sum per warp) against the queue-driven k_poly1
+    """k_poly1s (k_plan's compacted self-contained item list, static schedule, raw keys one item ahead by cp.async,
+    samples one trip ahead in registers, one partial sum per warp, the left-over samples in poly_frame) against the
+    queue-driven k_poly1
     (ATSC_POLY1_STATIC=0): same per-sample arithmetic, another summation tree -- same records and payload bytes,
     errors equal to 1e-12 relative; non-tame frames (zeros, sign changes, NaN), constant frames between the big
-    ones (dropped by the prep kernel) and lengths that move the item boundaries included; vs the oracle too."""
+    ones (never listed by k_plan) and lengths that move the item boundaries included; vs the oracle too."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
