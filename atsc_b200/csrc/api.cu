@@ -115,6 +115,7 @@ struct Device {
     int front = 2;
     bool probe_kernel = true;  // ATSC_PROBE_KERNEL=0: k_fft_fwd runs the probe tails of k_sfold's frames itself
     bool poly_items = true;  // ATSC_POLY_ITEMS=0: k_poly evaluates the first step of the big frames itself
+    int poly_items_maxf = 3;  // ATSC_POLY_ITEMS_MAXF: items only while the big frames number at most this many per k_poly CTA slot
     bool poly1_static = true;  // ATSC_POLY1_STATIC=0: the queue-driven k_poly1 instead of k_poly1_prep + k_poly1s (A/B runs)
     bool front_poly = true;  // ... including the first Polynomial step (ATSC_FRONT_POLY=0: k_poly does it)
     bool front_fold = true;  // ... including the FFT probe (ATSC_FRONT_FOLD=0: k_fft_fwd's own probe reads the samples again)
@@ -464,6 +465,7 @@ int device_init(Device &D) {
     D.front_poly = env_int("ATSC_FRONT_POLY", 1, 0, 1) != 0;
     D.poly_items = env_int("ATSC_POLY_ITEMS", 1, 0, 1) != 0;
     D.poly1_static = env_int("ATSC_POLY1_STATIC", 1, 0, 1) != 0;
+    D.poly_items_maxf = env_int("ATSC_POLY_ITEMS_MAXF", 3, 0, 1 << 20);
     D.probe_kernel = env_int("ATSC_PROBE_KERNEL", 1, 0, 1) != 0;
     D.sms = sms;
     if ((rc = engine_init(D, D.eng[0], sms))) return rc;  // the others are set up when a call first needs them
@@ -594,7 +596,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
                 n_pitems += poly_item_count(reqs[i].len);
                 n_pframes++;
             }
-    if (n_pframes > 3u * (size_t)E.pool.poly_slots) n_pitems = 0;
+    if (n_pframes > (size_t)D.poly_items_maxf * (size_t)E.pool.poly_slots) n_pitems = 0;
     hcap = E.pitems_cap;
     if ((rc = grow(D, E.st, E.d_pitems, E.pitems_cap, n_pitems))) return rc;
     if ((rc = grow(D, E.st, E.h_pitems, hcap, E.pitems_cap, true))) return rc;

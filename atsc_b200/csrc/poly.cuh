@@ -342,37 +342,63 @@ __device__ __forceinline__ void p1_load_trip(double (&o)[POLY_NS], const double 
 #pragma unroll
     for (int u = 0; u < POLY_NS; u++) o[u] = __ldg(p + (uint32_t)u * P1_STEP);
 }
-// The segment loop of one item for one thread (offset j of group g); returns its share of the MAPE sum.
-// o_nxt holds the samples of the item's first trip on entry (loaded while the previous item finished) and is
-// refilled one trip ahead inside the loop: the FP64 work of a trip covers the latency of the next trip's loads.
+// One trip of k_poly1s' segment loop: the MAPE terms of this thread's NS samples o[] against the Hermite values of
+// the NS segments whose (key, tangent) pairs start at kp.
+// TAME frames (poly_tame) take the guard-free arithmetic, with one more saving: every sample has the sign of vmin,
+// so the rounding addend copysign(pred(0.5), y) of round_half_away is the same for the whole frame (`half`).  A
+// spline value that overshoots across zero gets the wrong-signed addend; its rounded value still lies on the far
+// side of zero from [vmin, vmax] (|vmin|, |vmax| >= 1e-200) and is clamped to the same bound as the exact one.
 template <bool TAME>
-__device__ __forceinline__ double p1_item_loop(const P1Item &I, const double2 *kp, double (&o_nxt)[POLY_NS], bool active,
+__device__ __forceinline__ double p1_trip(const double2 *kp, const double (&o)[POLY_NS], double vmin, double vmax, double half,
+                                          double h00, double h10, double h01, double h11) {
+    constexpr int NS = POLY_NS;
+    double e[NS];
+    double2 kv[NS + 1];
+#pragma unroll
+    for (int u = 0; u <= NS; u++) kv[u] = kp[u];
+#pragma unroll
+    for (int u = 0; u < NS; u++) {
+        const double v = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(kv[u].x, h00), __dmul_rn(kv[u].y, h10)), __dmul_rn(kv[u + 1].x, h01)),
+                                   __dmul_rn(kv[u + 1].y, h11));
+        if (TAME) {
+            double out = div_1e5_int53(trunc(__dadd_rn(__dmul_rn(v, 100000.0), half)));
+            out = out < vmin ? vmin : (out > vmax ? vmax : out);
+            e[u] = mape_term_tame(out, o[u]);
+        } else {
+            e[u] = mape_term(round_and_limit5_fast(v, vmin, vmax), o[u]);
+        }
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int u = 0; u < NS; u++) acc += e[u];
+    return acc;
+}
+// The segment loop of one item for one thread (offset j of group g); returns its share of the MAPE sum.
+// oA holds the samples of the item's first trip on entry (loaded while the previous item finished); inside the
+// loop the next trip's samples are loaded one trip ahead, alternating between two register sets (two trips per
+// round, no copies): the FP64 work of a trip covers the latency of the next trip's loads.
+template <bool TAME>
+__device__ __forceinline__ double p1_item_loop(const P1Item &I, const double2 *kp, double (&oA)[POLY_NS], bool active,
                                                uint32_t g, uint32_t j, double h00, double h10, double h01, double h11) {
     constexpr int NS = POLY_NS;
+    constexpr size_t TRIP = (size_t)NS * P1_G * P1_STEP;  // samples between two trips of a thread
     const double vmin = I.vmin, vmax = I.vmax;
+    const double half = copysign(0.49999999999999994, vmin);
     const uint32_t b_hi = I.b_hi;
     const double *po = I.d + (size_t)(1u + NS * (I.b_lo + g)) * P1_STEP + j;  // this thread's samples of the current trip
     double acc = 0.0;
+    double oB[NS];
     // (the lanes beyond the fifth group make no trip but stay on the same path: barriers and shuffles are warp-wide)
-    for (uint32_t qq = active ? I.b_lo + g : b_hi; qq < b_hi; qq += P1_G) {
-        double o[NS], e[NS];
-        double2 kv[NS + 1];
-#pragma unroll
-        for (int u = 0; u < NS; u++) o[u] = o_nxt[u];
-        po += (size_t)NS * P1_G * P1_STEP;
-        if (qq + P1_G < b_hi) p1_load_trip(o_nxt, po);
-#pragma unroll
-        for (int u = 0; u <= NS; u++) kv[u] = kp[u];
-#pragma unroll
-        for (int u = 0; u < NS; u++) {
-            const double v = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(kv[u].x, h00), __dmul_rn(kv[u].y, h10)), __dmul_rn(kv[u + 1].x, h01)),
-                                       __dmul_rn(kv[u + 1].y, h11));
-            e[u] = TAME ? mape_term_tame(round_and_limit5_tame(v, vmin, vmax), o[u]) : mape_term(round_and_limit5_fast(v, vmin, vmax), o[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < NS; u++) acc += e[u];
-        kp += NS * P1_G;
+    uint32_t qq = active ? I.b_lo + g : b_hi;
+    for (; qq + P1_G < b_hi; qq += 2u * P1_G) {
+        p1_load_trip(oB, po + TRIP);
+        acc += p1_trip<TAME>(kp, oA, vmin, vmax, half, h00, h10, h01, h11);
+        po += 2u * TRIP;
+        if (qq + 2u * P1_G < b_hi) p1_load_trip(oA, po);
+        acc += p1_trip<TAME>(kp + NS * P1_G, oB, vmin, vmax, half, h00, h10, h01, h11);
+        kp += 2u * NS * P1_G;
     }
+    if (qq < b_hi) acc += p1_trip<TAME>(kp, oA, vmin, vmax, half, h00, h10, h01, h11);  // odd trip count
     return acc;
 }
 

@@ -263,6 +263,14 @@ def test_poly1_static_matches_items():
             cs.append((f"util{n}", gen.make("util", n, n)))
             cs.append((f"const{n}", np.full(n, 3.25)))
             cs.append((f"sign{n}", np.sin(np.arange(n) / 900.0) * 3.0 + rng.normal(0, 0.01, n)))  # not tame
+        # tame frames (one sign, away from zero) whose spline overshoots ACROSS zero between spikes at the key
+        # positions: k_poly1s rounds them with the frame's sign (poly.cuh: p1_trip), the clamp must hide it
+        for n, sgn in ((131072, 1.0), (100000, -1.0), (65536, 1.0)):
+            a = np.full(n, 0.001)
+            a[::300] = 10.0
+            a[150::300] = 0.004
+            a += rng.uniform(0, 1e-6, n)
+            cs.append((f"overshoot{n}_{int(sgn)}", sgn * a))
         # enough items that every CTA of k_poly1s walks several (descriptor / key double buffering, ring hand-over)
         for i in range(12):
             cs.append((f"periodic131072_{i}", gen.make("periodic", 131072, 100 + i)))
