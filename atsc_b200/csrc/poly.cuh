@@ -377,6 +377,9 @@ __device__ __forceinline__ double p1_trip(const double2 *kp, const double (&o)[P
 // oA holds the samples of the item's first trip on entry (loaded while the previous item finished); inside the
 // loop the next trip's samples are loaded one trip ahead, alternating between two register sets (two trips per
 // round, no copies): the FP64 work of a trip covers the latency of the next trip's loads.
+#ifndef P1_L2_AHEAD
+#define P1_L2_AHEAD 3u
+#endif
 template <bool TAME>
 __device__ __forceinline__ double p1_item_loop(const P1Item &I, const double2 *kp, double (&oA)[POLY_NS], bool active,
                                                uint32_t g, uint32_t j, double h00, double h10, double h01, double h11) {
@@ -392,6 +395,12 @@ __device__ __forceinline__ double p1_item_loop(const P1Item &I, const double2 *k
     uint32_t qq = active ? I.b_lo + g : b_hi;
     for (; qq + P1_G < b_hi; qq += 2u * P1_G) {
         p1_load_trip(oB, po + TRIP);
+        if (P1_L2_AHEAD && qq + (P1_L2_AHEAD + 1u) * P1_G < b_hi) {
+            // the trips P1_L2_AHEAD and P1_L2_AHEAD + 1 from now: on their way into L2, no register held
+#pragma unroll
+            for (int u = 0; u < 2 * NS; u++)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(po + P1_L2_AHEAD * TRIP + (u >> 2) * TRIP + (uint32_t)(u & 3) * P1_STEP));
+        }
         acc += p1_trip<TAME>(kp, oA, vmin, vmax, half, h00, h10, h01, h11);
         po += 2u * TRIP;
         if (qq + 2u * P1_G < b_hi) p1_load_trip(oA, po);
