@@ -587,7 +587,9 @@ def main():
     dom_ms = kms[dom] / args.steps
     front_mode = os.environ.get("ATSC_FRONT", "2")  # api.cu: 2 = k_sfold (default), 1 = k_front, 0 = separate passes
     kname = {"front": "k_sfold" if front_mode == "2" else "k_front",
-             "poly": "k_poly1+k_poly" if os.environ.get("ATSC_POLY_ITEMS", "1") != "0" else "k_poly"}
+             "poly": "k_poly" if os.environ.get("ATSC_POLY_ITEMS", "1") == "0" else
+                     "k_plan+k_poly1s+k_poly" if os.environ.get("ATSC_POLY1_STATIC", "1") != "0" else "k_plan+k_poly1+k_poly"}
+    p1name = "k_poly1s" if os.environ.get("ATSC_POLY1_STATIC", "1") != "0" else "k_poly1"
     big_samples = int(lens[lens >= 16384].astype(np.int64).sum())  # the frames the front-end kernel takes
     fftwin_samples = int(lens[comps == atsc_b200.FFT].astype(np.int64).sum())  # frames k_fft_fwd transforms in full
     dom_samples = {"stats": n_samples - (big_samples if front_mode != "0" else 0), "select": n_samples, "front": big_samples,
@@ -620,10 +622,11 @@ def main():
     traffic, traffic_detail = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if dom == "poly" and "k_poly1" in tj and os.environ.get("ATSC_POLY_ITEMS", "1") != "0":
-            # the 'poly' slot times k_plan + k_poly1 + k_poly: one wave's launches of both kernels
-            traffic_detail = {"k_poly1": tj["k_poly1"], "k_poly": {k: v for k, v in tj["k_poly"].items() if k != "whole_frames"}}
-            traffic = tj["k_poly1"]["bytes_per_launch"] + tj["k_poly"]["bytes_per_launch"]
+        if dom == "poly" and p1name in tj and os.environ.get("ATSC_POLY_ITEMS", "1") != "0":
+            # the 'poly' slot times k_plan + k_poly1s + k_poly: one wave's launches of the two sample-reading kernels
+            pk = "k_poly_after_poly1s" if p1name == "k_poly1s" and "k_poly_after_poly1s" in tj else "k_poly"
+            traffic_detail = {p1name: tj[p1name], "k_poly": {k: v for k, v in tj[pk].items() if k != "whole_frames"}}
+            traffic = tj[p1name]["bytes_per_launch"] + tj[pk]["bytes_per_launch"]
         else:
             traffic_detail = tj.get(kname.get(dom, "k_" + dom))
             if traffic_detail:
@@ -640,7 +643,7 @@ def main():
     if iso and "error" not in iso:
         iso1 = dict(iso)
         iso1["stats"] = iso.get("stats", 0.0) + iso.get("front", 0.0)
-        names1 = {"stats": "k_stats" if front_mode == "0" else "k_stats+" + kname["front"], "poly": "k_poly+k_poly1",
+        names1 = {"stats": "k_stats" if front_mode == "0" else "k_stats+" + kname["front"], "poly": kname["poly"],
                   "fft_fwd": "k_fft_fwd"}
         one_engine = {names1[k]: {"ms_per_288_series": round(iso1[k], 4), "achieved": alg1[k] / (iso1[k] * 1e-3) / 1e9,
                                   "frac": alg1[k] / (iso1[k] * 1e-3) / 1e9 / peak}
@@ -656,9 +659,18 @@ def main():
                         "(waves of several engines overlap, so these durations include contention and add up to more "
                         "than the step); one_engine: the same kernels on a 288-series call with a single engine, i.e. each "
                         "launch alone on the GPU, which is the figure to hold against the kernel's own roofline (k_sfold / k_front "
-                        "are reported under 'front'; 'poly' covers k_plan + k_poly1 + k_poly); k_poly and k_fft_fwd wait on "
-                        "loads (ncu long-scoreboard stalls), the stats pass runs nearer the HBM line (DESIGN.md section 4); "
-                        "the HBM line is the task's stated denominator"}
+                        "are reported under 'front'; 'poly' covers k_plan + k_poly1s + k_poly); the Polynomial step is bound by the "
+                        "schedulers' issue ports, not by HBM: 19 FP64 instructions per sample, each holding its port for two "
+                        "cycles (issue_model below, tools/ubench/p1arith.cu), the stats pass runs nearer the HBM line (DESIGN.md "
+                        "section 4); the HBM line is the task's stated denominator",
+                "issue_model": {
+                    "kernel": "k_poly1s",
+                    "cycles_per_4_samples_per_warp": 194,
+                    "derivation": "118 instructions per trip of 4 samples, 76 of them FP64 (2 issue cycles each on B200): 2 * 76 + 42",
+                    "samples_per_cycle_per_sm_at_full_issue": 4 * 32 * 4 / 194.0,
+                    "ubench_samples_per_cycle_per_sm": 2.6,
+                    "hbm_equivalent_gbs_at_full_issue": 4 * 32 * 4 / 194.0 * 148 * 1.965 * 8,
+                    "source": "tools/ubench/p1arith.cu on B200 (arithmetic from registers only), profiles/r2_p1_variants.md"}}
 
     # ---- decompression of the fleet just produced (device-resident output)
     frames_in = []
