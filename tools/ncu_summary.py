@@ -40,7 +40,7 @@ ci = next(i for i, c in enumerate(h) if c.startswith("# Samples") or c == "Warp 
 ii = next((i for i, c in enumerate(h) if c.startswith("Instructions Executed")), None)
 agg = collections.Counter(); ins = collections.Counter()
 for r in rows[hi + 1:]:
-    if len(r) <= ci: continue
+    if len(r) <= max(ci, ii or 0): continue  # rows of the next kernel's header block are shorter
     try:
         agg[r[si].strip()] += float(r[ci] or 0)
         if ii is not None: ins[r[si].strip()] += float(r[ii] or 0)
