@@ -24,9 +24,9 @@ r = j['roofline']
 rows.append(("C4 auto `-c 0`, 1152 × 1 M per GPU (subsample of 100 k × 1 M)", "const / periodic / noisy gauge", "1", f(j['value']),
              f(j['decompress']['value']) + " (decompress of the same fleet)",
              f"{100*r['whole_step_frac']:.1f} whole step; dominant slot `{r['kernel']}` {100*r['frac']:.1f} in-pipeline",
-             "`k_poly1` fp64 pipe 49 %, `k_sfold` 17 % (`r2_final_k_sfold_k_poly1_k_poly_k_fft_fwd_full.md`)",
+             "`k_poly1s` fp64 pipe 63 % = issue port 87 % busy, `k_sfold` fp64 17 % (`r2_final_k_sfold_k_plan_k_poly1s_k_poly_full.md`, `r2_p1_variants.md`)",
              f"{j['cpu_baseline']['value']:.1f} ({j['cpu_baseline']['cores']})"))
-rows.append(("C4 auto `-c 0`, 8 × 1152 × 1 M (build before `k_probe`)", "same", "8", f(n8['value']), f(n8['decompress']['value']),
+rows.append(("C4 auto `-c 0`, 8 × 1152 × 1 M (build before `k_probe` / `k_poly1s`)", "same", "8", f(n8['value']), f(n8['decompress']['value']),
              f"{100*n8['value']*8e6/(8*6529.1e9):.1f} of 8 × the HBM line", "same kernels", "—"))
 k = c['C4_auto_c6_288x1M']
 rows.append(("C4 auto `-c 6`, 288 × 1 M", "same", "1", f(k['msamples_per_s']), "—", f"{100*k['frac_of_hbm_line']:.1f}",
