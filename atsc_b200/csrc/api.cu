@@ -76,7 +76,7 @@ struct Engine {
     float4 *d_fold = nullptr;  // k_sfold's probe folds, SF_FOLD_SLOTS per frame (sfold.cuh)
     size_t fold_cap = 0;
     std::vector<uint8_t> fronted;  // issue_wave scratch
-    ChunkRef *d_pitems = nullptr, *h_pitems = nullptr;  // k_poly1 work items (frame, part)
+    ChunkRef *d_pitems = nullptr, *h_pitems = nullptr;  // (frame, part) work items of the queue-driven k_poly1 (ATSC_POLY1_STATIC=0)
     double *d_ppart = nullptr;                          // their partial MAPE sums (P1_PARTS per item with k_poly1s)
     P1Item *d_p1list = nullptr;                         // k_plan's compacted item descriptors for k_poly1s
     size_t pitems_cap = 0, ppart_cap = 0, p1list_cap = 0;
@@ -582,7 +582,7 @@ int issue_wave(Device &D, Engine &E, const double *d_samples, const std::vector<
             n_items++;
         }
     }
-    // frames whose first Polynomial step k_poly1 evaluates in balanced work items (poly.cuh)
+    // frames whose first Polynomial step k_poly1s (or k_poly1) evaluates in balanced work items (poly.cuh)
     auto poly1_frame = [&](const FrameReq &r) {
         return D.poly_items && r.len >= POLY_ITEM_MIN_LEN && poly_first_step(r.len) == P1_STEP && r.bounded && !r.select_only &&
                (r.comp == C_POLY || (r.comp == C_AUTO && (r.forced == 0xFF || r.forced == C_POLY)));

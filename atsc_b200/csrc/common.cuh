@@ -28,9 +28,9 @@ constexpr uint8_t FRES_POLY1 = 1;
 // ... k_probe found enough nonzero bins and the FFT candidate is NOT pruned: k_fft_fwd goes straight to the transform
 constexpr uint8_t FRES_SURVIVOR = 4;
 
-// k_poly1 (poly.cuh: poly_first_step_item): work items of the first Polynomial step of the big frames
+// k_poly1s / k_poly1 (poly.cuh): work items of the first Polynomial step of the big frames
 constexpr uint32_t POLY_ITEM = 32768;          // samples per item
-constexpr uint32_t POLY_ITEM_MIN_LEN = 65536;  // frames this long go through k_poly1 (step 100, >= 2 items)
+constexpr uint32_t POLY_ITEM_MIN_LEN = 65536;  // frames this long go through k_poly1s (step 100, >= 2 items)
 __host__ __device__ inline uint32_t poly_item_count(uint32_t N) { return (N + POLY_ITEM - 1) / POLY_ITEM; }
 // the step Polynomial::compress_bounded tries first
 __host__ __device__ inline uint32_t poly_first_step(uint32_t N) {
@@ -39,6 +39,15 @@ __host__ __device__ inline uint32_t poly_first_step(uint32_t N) {
     return step < 1 ? 1 : step;
 }
 constexpr uint32_t POLY_ITEM_KEYS = 352;       // keys / tangents of one item (<= 82 blocks of 4 segments + the tail)
+// Part q of the Q = poly_item_count(N) parts of a frame's first step (step 100): the four-segment blocks [b_lo, b_hi) of the
+// nblk = (K - 3) / 4 whole blocks that cover the Catmull-Rom segments 1 .. 4 * nblk (K keys: polynomial.rs:329-340); the
+// segments 4 * nblk + 1 .. K - 3 and the Linear ends are poly_first_step_rest's.
+__host__ __device__ inline void p1_item_blocks(uint32_t N, uint32_t q, uint32_t *b_lo, uint32_t *b_hi) {
+    const uint32_t kreg = (N + 99u) / 100u, K = kreg + (((kreg - 1u) * 100u != N - 1u) ? 1u : 0u);
+    const uint32_t Q = poly_item_count(N), nblk = (K - 3u) / 4u;
+    *b_lo = (uint32_t)((uint64_t)nblk * q / Q);
+    *b_hi = (uint32_t)((uint64_t)nblk * (q + 1u) / Q);
+}
 // k_poly1s (poly.cuh): self-contained descriptors of its work items, appended by k_plan
 constexpr uint32_t P1_STEP = 100;
 constexpr int P1_T = 512;                           // threads of k_poly1s: five groups of 100
@@ -94,7 +103,7 @@ struct FrameWork {
     uint32_t fwd_done;   // k_fft_fwd left the half spectrum + keys at spec_off
     uint32_t chunk0;     // first entry of this frame in the wave's stats chunk table
     uint32_t fold_slot;  // FM_SFOLD: this frame's block of the wave's fold arena
-    uint32_t poly_part0, poly_parts;  // k_poly1: first entry / number of this frame's first-step partial sums (0: none)
+    uint32_t poly_part0, poly_parts;  // k_poly1s / k_poly1: first item / number of items of this frame's first-step partial sums (0: none)
     uint64_t spec_off;   // entry offset into the wave's spectrum arena (~0 = frame not eligible for fft2.cuh)
     // ---- result
     uint8_t winner, near_tie;

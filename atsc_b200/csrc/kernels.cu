@@ -75,17 +75,14 @@ __global__ void k_plan(FrameWork *fr, uint32_t n, const double *__restrict__ sam
     // "same max and min"), cut into poly_parts balanced ranges of four-segment blocks (poly.cuh)
     if (p1_list && fw->poly_parts && fw->need_poly && !fw->poly_type && !fw->poly_valid && fw->bounded && fw->vmax != fw->vmin) {
         const uint32_t N = fw->len, Q = fw->poly_parts;
-        const PolyKeys k = poly_keys(N, P1_STEP);  // poly_first_step(N) == 100: the host lists no other frame
-        const uint32_t nblk = (k.K - 3) / POLY_NS;
-        const unsigned slot0 = atomicAdd(p1_count, Q);
+        const unsigned slot0 = atomicAdd(p1_count, Q);  // (poly_first_step(N) == 100: the host lists no other frame)
         for (uint32_t q = 0; q < Q; q++) {
             P1Item I;
             I.d = samples + fw->off;
             I.vmin = fw->vmin;
             I.vmax = fw->vmax;
             I.N = N;
-            I.b_lo = (uint32_t)((uint64_t)nblk * q / Q);
-            I.b_hi = (uint32_t)((uint64_t)nblk * (q + 1) / Q);
+            p1_item_blocks(N, q, &I.b_lo, &I.b_hi);
             I.out = fw->poly_part0 + q;
             I.nkeys = POLY_NS * (I.b_hi - I.b_lo) + 1;
             I.tame = poly_tame(fw->vmin, fw->vmax) ? 1u : 0u;

@@ -272,7 +272,8 @@ __device__ inline double poly_mape(const double *__restrict__ d, const PolyKeys 
     return __ddiv_rn(s, (double)N);
 }
 
-// k_poly1: the FIRST candidate step of a big bounded Catmull-Rom frame, cut into POLY_ITEM-sample work items so
+// k_poly1 (queue-driven predecessor of k_poly1s, kept for A/B runs): the FIRST candidate step of a big bounded
+// Catmull-Rom frame, cut into POLY_ITEM-sample work items so
 // that the pass balances over the SMs (a wave of the bench fleet holds ~340 full frames for 296 CTA slots: whole
 // frames leave a quarter of the SM time idle).  Item q of Q = poly_item_count(N) takes the NS-blocks
 // [nblk * q / Q, nblk * (q + 1) / Q) of the step poly_frame tries first, the last item also the left-over segments

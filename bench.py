@@ -634,7 +634,7 @@ def main():
     except Exception:
         pass
     # algorithmic bytes of a 288-series call: every sample once for the stats pass (k_stats + the front-end kernel),
-    # the non-constant frames for k_poly (+ k_poly1), the frames transformed in full for k_fft_fwd
+    # the non-constant frames for k_poly1s + k_poly, the frames transformed in full for k_fft_fwd
     per_series = 288.0 / S
     alg1 = {"stats": 288 * SERIES_LEN * 8, "poly": 192 * SERIES_LEN * 8}
     if front_mode == "0":  # with k_sfold + k_probe the forward kernel only sees surviving frames: a latency chain, no roofline

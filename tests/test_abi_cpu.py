@@ -90,3 +90,21 @@ def test_bulk_async_staging_in_the_shipped_sass():
     assert "SYNCS" in text, "no mbarrier transaction instruction in the SASS"
     # k_poly1s (the default first-step kernel) stages its samples with per-thread asynchronous copies
     assert "LDGSTS" in text, "no cp.async (LDGSTS) in the SASS"
+
+
+def test_first_step_partition_covers_every_sample(tmp_path):
+    """k_plan's work items for k_poly1s (common.cuh: poly_first_step, poly_item_count, p1_item_blocks): for every frame
+    length 65536 .. 131072 the items tile the four-segment blocks, fit the kernel's key buffers, and with
+    poly_first_step_rest's share cover each sample of the frame exactly once (polynomial.rs:218-221, 329-349).
+    Host code compiled from the product's own header; no GPU needed."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "p1_partition_check")
+    subprocess.check_call([nvcc, "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", os.path.join(root, "atsc_b200", "csrc"),
+                           "-o", exe, os.path.join(root, "tools", "p1_partition_check.cu")], timeout=300)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr

@@ -1,6 +1,7 @@
 """The front ends of the big frames against each other and against the CPU oracle: k_front (ATSC_FRONT=1: stats +
 first Polynomial step + FFT probe fold in one read), k_sfold (ATSC_FRONT=2, the default: stats + probe fold, with
-k_probe), the separate passes (ATSC_FRONT=0), and k_poly1's work items: same frame records, same payload bytes.
+k_probe), the separate passes (ATSC_FRONT=0), and the first-step work items (k_poly1s, k_poly1): same frame records,
+same payload bytes.
 Reference behaviour under test: frame/mod.rs:71-149, polynomial.rs:209-277, optimizer/utils.rs:39-89."""
 import os
 
@@ -201,7 +202,7 @@ def test_sfold_mixed_batch_and_other_compressors(sfold_ctxs):
 
 @pytest.fixture(scope="module")
 def poly_item_ctxs():
-    """k_poly1 (first Polynomial step of frames >= 65536 samples in balanced work items, poly.cuh) on / off."""
+    """First Polynomial step of frames >= 65536 samples in balanced work items (k_poly1s, poly.cuh) on / off."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
